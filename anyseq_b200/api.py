@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's operator surface for the DP hot path.
+
+Names follow the reference: alignment schemes ``global`` / ``semiglobal`` /
+``local`` (src/align.impala:96-124), scoring schemes ``linear_scoring_scheme`` /
+``affine_scoring_scheme`` (src/align.impala:144-166), operators ``score`` and
+``traceback_lintime`` (src/align.impala:218-271) and the six exported entry
+points of src/export.impala.  Everything executes in libanyseq_b200.so (CUDA,
+sm_100a) through the C ABI of include/anyseq.h; nothing here computes a DP cell.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import AnyseqError, Result, Scoring, StripPartial, as_u8, make_scoring
+
+
+@dataclass(frozen=True)
+class ScoringScheme:
+    same: int = 2
+    diff: int = -1
+    gap_init: int = 0       # 0 => linear gaps
+    gap_extend: int = -1
+
+    @property
+    def affine(self) -> bool:
+        return self.gap_init != 0
+
+
+def linear_scoring_scheme(same: int = 2, diff: int = -1, gap: int = -1) -> ScoringScheme:
+    """linear_scoring_scheme(same, diff, gap): src/align.impala:144-150."""
+    return ScoringScheme(same, diff, 0, gap)
+
+
+def affine_scoring_scheme(same: int = 2, diff: int = -1, gap_init: int = -2, gap_extend: int = -1) -> ScoringScheme:
+    """affine_scoring_scheme(same, diff, gapInit, gapExtend): src/align.impala:153-166
+    (parameter names only -- Gotoh as defined in DESIGN.md)."""
+    return ScoringScheme(same, diff, gap_init, gap_extend)
+
+
+REFERENCE_SCORING = linear_scoring_scheme(2, -1, -1)   # src/export.impala:14
+
+
+@dataclass
+class AlignmentResult:
+    score: int
+    end_i: int
+    end_j: int
+    kernel_ms: float
+    kernel_launches: int
+    aligned_query: bytes | None = None
+    aligned_subject: bytes | None = None
+
+    def cigar(self) -> str:
+        if self.aligned_query is None:
+            raise ValueError("no traceback in this result")
+        return cigar(self.aligned_query, self.aligned_subject)
+
+
+def cigar(aligned_query: bytes, aligned_subject: bytes) -> str:
+    L = capi.load_library()
+    a, b = as_u8(aligned_query), as_u8(aligned_subject)
+    need = -L.anyseq_cigar(capi._ptr(a), capi._ptr(b), len(a), None, 0)
+    buf = C.create_string_buffer(int(need))
+    n = L.anyseq_cigar(capi._ptr(a), capi._ptr(b), len(a), buf, need)
+    return buf.raw[:n].decode("ascii")
+
+
+class Aligner:
+    """One engine per (process, GPU): wraps an ``anyseq_ctx``."""
+
+    def __init__(self, device: int = -1):
+        self._lib = capi.load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.anyseq_ctx_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise AnyseqError(rc, self._err())
+
+    def _err(self) -> str:
+        m = self._lib.anyseq_last_error()
+        return m.decode() if m else ""
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise AnyseqError(rc, self._err())
+
+    def close(self):
+        if self._ctx:
+            self._lib.anyseq_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    def tune(self, cols_per_lane: int = 0, band_rows: int = 0, blocks_per_sm: int = 0, watchdog_ms: int = 0):
+        self._check(self._lib.anyseq_ctx_tune(self._ctx, cols_per_lane, band_rows, blocks_per_sm, watchdog_ms))
+
+    def device_info(self):
+        sm, rw = C.c_int(), C.c_int()
+        name = C.create_string_buffer(64)
+        self._check(self._lib.anyseq_device_info(self._ctx, C.byref(sm), C.byref(rw), name))
+        return {"sm_count": sm.value, "resident_warps": rw.value, "name": name.value.decode()}
+
+    # -- score(): src/align.impala:218-235 ---------------------------------
+    def score(self, mode, query, subject, scoring: ScoringScheme = REFERENCE_SCORING) -> AlignmentResult:
+        q, s = as_u8(query), as_u8(subject)
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        self._check(self._lib.anyseq_score(self._ctx, C.byref(sc), capi._ptr(q), len(q), capi._ptr(s), len(s),
+                                           C.byref(res)))
+        return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches)
+
+    def score_device(self, mode, d_query: int, lenq: int, d_subject: int, lens: int,
+                     scoring: ScoringScheme = REFERENCE_SCORING) -> AlignmentResult:
+        """Sequences already resident in HBM (raw device pointers, e.g. tensor.data_ptr())."""
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        self._check(self._lib.anyseq_score_device(self._ctx, C.byref(sc), C.c_void_p(d_query), lenq,
+                                                  C.c_void_p(d_subject), lens, C.byref(res)))
+        return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches)
+
+    # -- traceback_lintime(): src/align.impala:237-271 ---------------------
+    def align(self, mode, query, subject, scoring: ScoringScheme = REFERENCE_SCORING) -> AlignmentResult:
+        q, s = as_u8(query), as_u8(subject)
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        n = len(q) + len(s)
+        oq = np.zeros(max(n, 1), dtype=np.uint8)
+        os_ = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self._lib.anyseq_align(self._ctx, C.byref(sc), capi._ptr(q), len(q), capi._ptr(s), len(s),
+                                           capi._ptr(oq), capi._ptr(os_), C.byref(res)))
+        return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches,
+                               oq[:n].tobytes(), os_[:n].tobytes())
+
+    # -- batches of independent pairs --------------------------------------
+    def score_batch(self, mode, queries, q_off, subjects, s_off, scoring: ScoringScheme = REFERENCE_SCORING):
+        q, s = as_u8(queries), as_u8(subjects)
+        qo = np.ascontiguousarray(q_off, dtype=np.int64)
+        so = np.ascontiguousarray(s_off, dtype=np.int64)
+        npairs = len(qo) - 1
+        scores = np.zeros(max(npairs, 1), dtype=np.int32)
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        i64p = C.POINTER(C.c_int64)
+        self._check(self._lib.anyseq_score_batch(self._ctx, C.byref(sc), capi._ptr(q), qo.ctypes.data_as(i64p),
+                                                 capi._ptr(s), so.ctypes.data_as(i64p), npairs,
+                                                 scores.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(res)))
+        return scores[:npairs], AlignmentResult(res.score, -1, -1, res.kernel_ms, res.kernel_launches)
+
+    def score_batch_device(self, mode, d_queries: int, d_q_off: int, d_subjects: int, d_s_off: int, npairs: int,
+                           d_scores: int, scoring: ScoringScheme = REFERENCE_SCORING) -> AlignmentResult:
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        self._check(self._lib.anyseq_score_batch_device(self._ctx, C.byref(sc), C.c_void_p(d_queries),
+                                                        C.c_void_p(d_q_off), C.c_void_p(d_subjects),
+                                                        C.c_void_p(d_s_off), npairs, C.c_void_p(d_scores),
+                                                        C.byref(res)))
+        return AlignmentResult(res.score, -1, -1, res.kernel_ms, res.kernel_launches)
+
+    # -- roofline denominator ----------------------------------------------
+    def measure_int_peak(self, kind: int = 0):
+        ops, mhz = C.c_double(), C.c_float()
+        self._check(self._lib.anyseq_measure_int_peak(self._ctx, kind, C.byref(ops), C.byref(mhz)))
+        return ops.value, mhz.value
+
+
+_default: Aligner | None = None
+
+
+def default_aligner() -> Aligner:
+    global _default
+    if _default is None:
+        _default = Aligner(-1)
+    return _default
+
+
+# The six exported entry points (src/export.impala:5-147 / src/import.h:14-41),
+# called through the very symbols a C host would link against.
+def _legacy_score(name: str, query, subject) -> int:
+    L = capi.load_library()
+    q, s = as_u8(query), as_u8(subject)
+    return int(getattr(L, name)(capi._ptr(q), len(q), capi._ptr(s), len(s)))
+
+
+def _legacy_construct(name: str, query, subject):
+    L = capi.load_library()
+    q, s = as_u8(query), as_u8(subject)
+    n = len(q) + len(s)
+    oq = np.full(max(n, 1), ord(" "), dtype=np.uint8)
+    os_ = np.full(max(n, 1), ord(" "), dtype=np.uint8)
+    r = int(getattr(L, name)(capi._ptr(q), len(q), capi._ptr(s), len(s), capi._ptr(oq), capi._ptr(os_)))
+    return r, oq[:n].tobytes(), os_[:n].tobytes()
+
+
+def global_alignment_score(query, subject) -> int:
+    return _legacy_score("global_alignment_score", query, subject)
+
+
+def semiglobal_alignment_score(query, subject) -> int:
+    return _legacy_score("semiglobal_alignment_score", query, subject)
+
+
+def local_alignment_score(query, subject) -> int:
+    return _legacy_score("local_alignment_score", query, subject)
+
+
+def construct_global_alignment(query, subject):
+    return _legacy_construct("construct_global_alignment", query, subject)
+
+
+def construct_semiglobal_alignment(query, subject):
+    return _legacy_construct("construct_semiglobal_alignment", query, subject)
+
+
+def construct_local_alignment(query, subject):
+    return _legacy_construct("construct_local_alignment", query, subject)

@@ -1,0 +1,139 @@
+"""ctypes binding of libanyseq_b200.so -- the C ABI declared in include/anyseq.h.
+
+This is the host-side mirror of the reference's operator surface for the hot
+path: the six legacy entry points of src/import.h:14-41 plus the parametrised
+scheme surface (alignment scheme x scoring scheme, src/align.impala:96-166).
+There is no CPU fallback: without the CUDA library / a GPU every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libanyseq_b200.so")
+
+GLOBAL, SEMIGLOBAL, LOCAL = 0, 1, 2
+MODES = {"global": GLOBAL, "semiglobal": SEMIGLOBAL, "local": LOCAL}
+
+# every symbol include/anyseq.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
+    "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
+    "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune",
+    "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_cigar",
+    "anyseq_score_batch", "anyseq_score_batch_device",
+    "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
+    "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_strip_combine",
+    "anyseq_measure_int_peak", "anyseq_device_info",
+]
+
+
+class Scoring(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("same", C.c_int32), ("diff", C.c_int32),
+                ("gap_init", C.c_int32), ("gap_extend", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("score", C.c_int64), ("end_i", C.c_int32), ("end_j", C.c_int32),
+                ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32)]
+
+
+class StripPartial(C.Structure):
+    _fields_ = [("row_best", C.c_int32), ("row_best_j", C.c_int32),
+                ("col_best", C.c_int32), ("col_best_i", C.c_int32),
+                ("local_best", C.c_int32), ("corner", C.c_int32),
+                ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32)]
+
+
+class AnyseqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"anyseq_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} is missing: build it with `python -m anyseq_b200.build` (nvcc, sm_100a). "
+            "anyseq_b200 has no CPU fallback.")
+    L = C.CDLL(p)
+    cp, vp, i64p = C.c_char_p, C.c_void_p, C.POINTER(C.c_int64)
+    for name in ("global_alignment_score", "semiglobal_alignment_score", "local_alignment_score"):
+        f = getattr(L, name)
+        f.restype = C.c_int64
+        f.argtypes = [vp, C.c_int, vp, C.c_int]
+    for name in ("construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment"):
+        f = getattr(L, name)
+        f.restype = C.c_int64
+        f.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    L.anyseq_ctx_create.restype = C.c_int
+    L.anyseq_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.anyseq_ctx_destroy.restype = None
+    L.anyseq_ctx_destroy.argtypes = [vp]
+    L.anyseq_last_error.restype = cp
+    L.anyseq_last_error.argtypes = []
+    L.anyseq_ctx_tune.restype = C.c_int
+    L.anyseq_ctx_tune.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.anyseq_score.restype = C.c_int
+    L.anyseq_score.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.POINTER(Result)]
+    L.anyseq_score_device.restype = C.c_int
+    L.anyseq_score_device.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.POINTER(Result)]
+    L.anyseq_align.restype = C.c_int
+    L.anyseq_align.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, vp, vp, C.POINTER(Result)]
+    L.anyseq_cigar.restype = C.c_int64
+    L.anyseq_cigar.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
+    L.anyseq_score_batch.restype = C.c_int
+    L.anyseq_score_batch.argtypes = [vp, C.POINTER(Scoring), vp, i64p, vp, i64p, C.c_int64,
+                                     C.POINTER(C.c_int32), C.POINTER(Result)]
+    L.anyseq_score_batch_device.restype = C.c_int
+    L.anyseq_score_batch_device.argtypes = [vp, C.POINTER(Scoring), vp, vp, vp, vp, C.c_int64, vp, C.POINTER(Result)]
+    L.anyseq_strip_inbox_create.restype = C.c_int
+    L.anyseq_strip_inbox_create.argtypes = [vp, C.c_int, C.POINTER(vp), vp]
+    L.anyseq_strip_inbox_open.restype = C.c_int
+    L.anyseq_strip_inbox_open.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.anyseq_strip_inbox_reset.restype = C.c_int
+    L.anyseq_strip_inbox_reset.argtypes = [vp, vp]
+    L.anyseq_strip_inbox_destroy.restype = None
+    L.anyseq_strip_inbox_destroy.argtypes = [vp, vp]
+    L.anyseq_score_strip_device.restype = C.c_int
+    L.anyseq_score_strip_device.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                            vp, vp, C.POINTER(StripPartial)]
+    L.anyseq_strip_combine.restype = C.c_int
+    L.anyseq_strip_combine.argtypes = [C.POINTER(Scoring), C.POINTER(StripPartial), C.c_int, C.POINTER(Result)]
+    L.anyseq_measure_int_peak.restype = C.c_int
+    L.anyseq_measure_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.anyseq_device_info.restype = C.c_int
+    L.anyseq_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]
+    if path is None:
+        _lib = L
+    return L
+
+
+def as_u8(a) -> np.ndarray:
+    """bytes / str / ndarray -> contiguous uint8 array (raw bytes, no case folding:
+    the reference compares symbols as bytes, src/align.impala:132)."""
+    if isinstance(a, str):
+        a = a.encode("latin-1")
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data if a.size else 0)
+
+
+def make_scoring(mode, same=2, diff=-1, gap_init=0, gap_extend=-1) -> Scoring:
+    m = MODES[mode] if isinstance(mode, str) else int(mode)
+    return Scoring(m, same, diff, gap_init, gap_extend)

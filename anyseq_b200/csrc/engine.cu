@@ -1,0 +1,410 @@
+// engine.cu -- score-only path: job construction, launches, result extraction.
+#include "engine.cuh"
+#include "strip_kernel.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace anyseq {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+// ---------------------------------------------------------------------------
+// border initialisation: create_scoring_matrix_linmem (src/scoring.impala:218-242)
+// and create_scoring_hb_matrix_linmem (:261-299) -- column/row/corner vectors
+// from init_scores (src/align.impala:85-86).  border(k) = H(k, -1) = H(-1, k).
+// ---------------------------------------------------------------------------
+__global__ void init_jobs_kernel(const Job* __restrict__ jobs, int njobs, ScoreParams sp, int SW,
+                                 int col0)
+{
+    for (int jb = blockIdx.y; jb < njobs; jb += gridDim.y) {
+        const Job J = jobs[jb];
+        const int wpad = J.nstrips * SW;
+        const int n = max(max(J.h, wpad), J.nstrips);
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+            if (idx < J.h) {
+                J.colH[idx] = J.init_global ? sp.gap_open + idx * sp.gap_extend : 0;
+                if (J.colE) J.colE[idx] = kNegInf;
+            }
+            if (idx < wpad) {
+                J.rowH[idx] = J.init_global ? sp.gap_open + (col0 + idx) * sp.gap_extend : 0;
+                if (J.rowF) J.rowF[idx] = kNegInf;
+            }
+            if (idx < J.nstrips) {
+                const int c = col0 + idx * SW - 1;   // column left of the strip
+                J.corner[idx] = (J.init_global && c >= 0) ? sp.gap_open + c * sp.gap_extend : 0;
+                J.progress[idx] = 0;
+            }
+            if (idx == 0 && J.best) *J.best = kScoreMin;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// result extraction: get_{global,semiglobal,local}_scoring_linmem
+// (src/scoring.impala:29-137).  reduce_max of the reference returns the LOWEST
+// index attaining the maximum (src/utils.impala:30-49,
+// src/iteration_cpu.impala:205-250); arg_max_lowest reproduces that.
+// ---------------------------------------------------------------------------
+__device__ void arg_max_lowest(const int* __restrict__ v, int n, int& best, int& best_i)
+{
+    __shared__ int s_v[32];
+    __shared__ int s_i[32];
+    int bv = kScoreMin, bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int x = __ldcg(v + i);
+        if (x > bv) { bv = x; bi = i; }   // ascending i per thread: first max kept
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) / 32;
+        bv = threadIdx.x < nw ? s_v[threadIdx.x] : kScoreMin;
+        bi = threadIdx.x < nw ? s_i[threadIdx.x] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+    }
+    __syncthreads();
+    best = bv;
+    best_i = bi;   // valid in thread 0
+}
+
+// out[0]=score out[1]=pos_i out[2]=pos_j ; partial (multi-GPU) results in out[3..7]:
+// row_best,row_best_j,col_best,col_best_i ; local_best in out[0]
+__global__ void finish_score_kernel(const Job* __restrict__ jobs, int mode, int col0, int n_total,
+                                    int* __restrict__ out)
+{
+    const Job J = jobs[0];
+    int rv, ri, cv, ci;
+    arg_max_lowest(J.rowH, J.w, rv, ri);
+    arg_max_lowest(J.colH, J.h, cv, ci);
+    if (threadIdx.x == 0) {
+        out[3] = rv; out[4] = ri + col0; out[5] = cv; out[6] = ci;
+        out[7] = __ldcg(J.colH + J.h - 1);
+        if (mode == kGlobal) {
+            out[0] = __ldcg(J.colH + J.h - 1);
+            out[1] = J.h - 1; out[2] = n_total - 1;
+        } else if (mode == kSemiglobal) {
+            // candidates -1 (value init = 0) come first and win ties
+            // (src/scoring.impala:51-63: row first, column only if strictly greater)
+            int score = kScoreMin, pi = -1, pj = -1;
+            int rs = rv, rj = ri + col0;
+            if (0 >= rs) { rs = 0; rj = -1; }
+            if (rs > score) { score = rs; pi = J.h - 1; pj = rj; }
+            int cs = cv, cidx = ci;
+            if (0 >= cs) { cs = 0; cidx = -1; }
+            if (cs > score) { score = cs; pi = cidx; pj = n_total - 1; }
+            out[0] = score; out[1] = pi; out[2] = pj;
+        } else {
+            out[0] = *J.best; out[1] = -1; out[2] = -1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------
+using KernelFn = void (*)(const KernelArgs);
+
+static KernelFn pick_kernel(bool local, bool affine, int K)
+{
+#define ANYSEQ_PICK(L, A)                                             \
+    switch (K) {                                                      \
+        case 4: return strip_kernel<L, A, 4>;                         \
+        case 8: return strip_kernel<L, A, 8>;                         \
+        case 16: return strip_kernel<L, A, 16>;                       \
+        case 32: return strip_kernel<L, A, 32>;                       \
+        default: return nullptr;                                      \
+    }
+    if (local) {
+        if (affine) { ANYSEQ_PICK(true, true) } else { ANYSEQ_PICK(true, false) }
+    } else {
+        if (affine) { ANYSEQ_PICK(false, true) } else { ANYSEQ_PICK(false, false) }
+    }
+#undef ANYSEQ_PICK
+    return nullptr;
+}
+
+int Engine::init(int dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_last_error("no CUDA device available (libanyseq_b200 has no CPU fallback)");
+        return ANYSEQ_ERR_NO_DEVICE;
+    }
+    if (dev < 0) ANYSEQ_CUDA_CHECK(cudaGetDevice(&dev));
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(dev));
+    device = dev;
+    cudaDeviceProp prop;
+    ANYSEQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    std::strncpy(name, prop.name, sizeof(name) - 1);
+    if (prop.major < 10) {
+        set_last_error(std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+        return ANYSEQ_ERR_NO_DEVICE;
+    }
+    ANYSEQ_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    ANYSEQ_CUDA_CHECK(cudaEventCreate(&ev0_));
+    ANYSEQ_CUDA_CHECK(cudaEventCreate(&ev1_));
+    if (misc_.ensure(sizeof(int) * kMiscWords)) return ANYSEQ_ERR_NO_DEVICE;
+    ANYSEQ_CUDA_CHECK(cudaMallocHost(&h_misc_, sizeof(int) * kMiscWords));
+    const char* env;
+    if ((env = std::getenv("ANYSEQ_K"))) tune.cols_per_lane = std::atoi(env);
+    if ((env = std::getenv("ANYSEQ_BAND"))) tune.band_rows = std::atoi(env);
+    if ((env = std::getenv("ANYSEQ_BLOCKS_PER_SM"))) tune.blocks_per_sm = std::atoi(env);
+    if ((env = std::getenv("ANYSEQ_WATCHDOG_MS"))) tune.watchdog_ms = std::atoi(env);
+    return ANYSEQ_OK;
+}
+
+void Engine::destroy()
+{
+    if (device >= 0) cudaSetDevice(device);
+    DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &colH_, &colE_, &rowH_, &rowF_, &corner_,
+                            &progress_, &jobs_, &misc_, &colH2_, &colE2_, &aux_, &aux2_, &pred_,
+                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_};
+    for (DeviceBuffer* b : bufs) b->release();
+    if (h_misc_) cudaFreeHost(h_misc_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+    h_misc_ = nullptr; ev0_ = ev1_ = nullptr; stream_ = nullptr;
+}
+
+int Engine::resident_warps(int K, bool local, bool affine)
+{
+    KernelFn fn = pick_kernel(local, affine, K);
+    if (!fn) return 0;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, 0) != cudaSuccess) return 0;
+    if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
+    return nb * kWarpsPerBlock * sm_count;
+}
+
+int Engine::pick_K(int n) const
+{
+    if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
+        tune.cols_per_lane == 32)
+        return tune.cols_per_lane;
+    if (n >= (1 << 21)) return 32;
+    if (n >= (1 << 18)) return 16;
+    if (n >= (1 << 15)) return 8;
+    return 4;
+}
+
+// Band height: enough (band, strip) items in flight to occupy every resident
+// warp (the wavefront over items holds about nstrips + band_h/lag of them) and
+// enough items per warp for balance.
+int Engine::pick_band(int m, int nstrips, int resident) const
+{
+    if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
+    const long long lag = 128;
+    long long need = std::max(0, resident - nstrips) * lag;
+    long long nb_bal = (64LL * resident + nstrips - 1) / nstrips;
+    long long bh_bal = std::max<long long>(m / std::max<long long>(nb_bal, 1), 2048);
+    long long bh = std::max(need, std::min<long long>(bh_bal, 1 << 16));
+    bh = std::min<long long>(bh, m);
+    bh = (bh + 31) / 32 * 32;
+    return (int)std::max<long long>(bh, 32);
+}
+
+// Launch init + strip kernels for a job list that is already in host memory.
+int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
+                     int* launches)
+{
+    const int njobs = (int)jobs.size();
+    long long total = 0;
+    for (Job& j : jobs) {
+        j.item_begin = total;
+        total += (long long)j.nstrips * j.nbands;
+    }
+    if (jobs_.ensure(sizeof(Job) * (size_t)njobs)) return ANYSEQ_ERR_NO_DEVICE;
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(jobs_.ptr, jobs.data(), sizeof(Job) * (size_t)njobs,
+                                      cudaMemcpyHostToDevice, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
+
+    KernelFn fn = pick_kernel(local, affine, K);
+    if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
+    int nb = 0;
+    ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, 0));
+    if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
+    if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
+    long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
+
+    {
+        int maxlen = 1;
+        for (const Job& j : jobs) maxlen = std::max(maxlen, std::max(j.h, j.nstrips * kWarp * K));
+        dim3 g((unsigned)std::min(1024, (maxlen + 255) / 256), (unsigned)std::min(njobs, 32768));
+        init_jobs_kernel<<<g, 256, 0, stream_>>>(jobs_.as<Job>(), njobs, sp, kWarp * K, init_col0_);
+        ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    }
+    KernelArgs ka;
+    ka.jobs = jobs_.as<Job>();
+    ka.njobs = njobs;
+    ka.total_items = total;
+    ka.sp = sp;
+    ka.status = misc_.as<int>() + kMiscStatus;
+    ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
+    void* args[] = {&ka};
+    ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, 0, stream_));
+    if (launches) *launches += 2;
+    return ANYSEQ_OK;
+}
+
+static int make_params(const anyseq_scoring& sc, ScoreParams* sp, bool* affine)
+{
+    if (sc.mode < 0 || sc.mode > 2 || sc.gap_init > 0 || sc.gap_extend > 0) {
+        set_last_error("bad scoring scheme (mode in 0..2, gap costs must be <= 0)");
+        return ANYSEQ_ERR_BAD_ARG;
+    }
+    *affine = sc.gap_init != 0;
+    sp->same = sc.same;
+    sp->diff = sc.diff;
+    sp->gap_extend = sc.gap_extend;
+    sp->gap_open = sc.gap_init + sc.gap_extend;   // linear: == gap
+    return ANYSEQ_OK;
+}
+
+// Degenerate inputs, following the reference's storage:
+// global -> the init value left in the column vector; semiglobal -> 0;
+// local -> SCORE_MIN (no block ever ran).
+static void empty_result(const anyseq_scoring& sc, int m, int n, anyseq_result* out)
+{
+    const int L = std::max(m, n);
+    int64_t v;
+    if (sc.mode == ANYSEQ_GLOBAL) v = L > 0 ? (int64_t)sc.gap_init + (int64_t)L * sc.gap_extend : 0;
+    else if (sc.mode == ANYSEQ_SEMIGLOBAL) v = 0;
+    else v = kScoreMin;
+    out->score = v;
+    out->end_i = m - 1;
+    out->end_j = n - 1;
+    out->kernel_ms = 0.f;
+    out->kernel_launches = 0;
+}
+
+int Engine::score_device(const anyseq_scoring& sc, const uint8_t* d_q, int m, const uint8_t* d_s, int n,
+                         anyseq_result* out)
+{
+    anyseq_strip_partial part;
+    if (m < 0 || n < 0 || !out) { set_last_error("bad lengths"); return ANYSEQ_ERR_BAD_ARG; }
+    if (m == 0 || n == 0) { empty_result(sc, m, n, out); return ANYSEQ_OK; }
+    int rc = score_strip_device(sc, d_q, m, d_s, 0, n, n, nullptr, nullptr, &part);
+    if (rc) return rc;
+    out->score = h_misc_[kMiscOut + 0];
+    out->end_i = h_misc_[kMiscOut + 1];
+    out->end_j = h_misc_[kMiscOut + 2];
+    out->kernel_ms = part.kernel_ms;
+    out->kernel_launches = part.kernel_launches;
+    return ANYSEQ_OK;
+}
+
+int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int m,
+                               const uint8_t* d_s_slice, int col_begin, int col_end, int n_total,
+                               Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out)
+{
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
+    ScoreParams sp;
+    bool affine;
+    int rc = make_params(sc, &sp, &affine);
+    if (rc) return rc;
+    const int w = col_end - col_begin;
+    if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
+    const bool local = sc.mode == ANYSEQ_LOCAL;
+    const int K = pick_K(w);
+    const int SW = kWarp * K;
+    if (inbox && (col_begin % SW) != 0) { set_last_error("strip boundary must be a multiple of the strip width"); return ANYSEQ_ERR_BAD_ARG; }
+    const int nstrips = (w + SW - 1) / SW;
+    const int resident = resident_warps(K, local, affine);
+    const int band_h = pick_band(m, nstrips, resident);
+
+    const size_t wpad = (size_t)nstrips * SW;
+    if (colH_.ensure(sizeof(int) * (size_t)m) || rowH_.ensure(sizeof(int) * wpad) ||
+        corner_.ensure(sizeof(int) * (size_t)nstrips) || progress_.ensure(sizeof(int) * (size_t)nstrips))
+        return ANYSEQ_ERR_NO_DEVICE;
+    if (affine && (colE_.ensure(sizeof(int) * (size_t)m) || rowF_.ensure(sizeof(int) * wpad)))
+        return ANYSEQ_ERR_NO_DEVICE;
+
+    Job J;
+    std::memset(&J, 0, sizeof(J));
+    J.q = d_q;
+    J.s = d_s_slice;
+    J.h = m;
+    J.w = w;
+    J.band_h = band_h;
+    J.nstrips = nstrips;
+    J.nbands = (m + band_h - 1) / band_h;
+    J.colH = colH_.as<int>();
+    J.colE = affine ? colE_.as<int>() : nullptr;
+    J.rowH = rowH_.as<int>();
+    J.rowF = affine ? rowF_.as<int>() : nullptr;
+    J.corner = corner_.as<int>();
+    J.progress = progress_.as<int>();
+    J.best = misc_.as<int>() + kMiscBest;
+    J.init_global = sc.mode == ANYSEQ_GLOBAL;
+    if (inbox) { J.inH = inbox->H(); J.inE = inbox->E(); J.in_progress = inbox->progress(); }
+    if (next_inbox) { J.outH = next_inbox->H(); J.outE = next_inbox->E(); J.out_progress = next_inbox->progress(); }
+
+    std::vector<Job> jobs(1, J);
+    int launches = 0;
+    init_col0_ = col_begin;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    rc = run_jobs(jobs, sp, local, affine, K, &launches);
+    init_col0_ = 0;
+    if (rc) return rc;
+    finish_score_kernel<<<1, 1024, 0, stream_>>>(jobs_.as<Job>(), sc.mode, col_begin, n_total,
+                                                  misc_.as<int>() + kMiscOut);
+    ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    launches += 1;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_, misc_.ptr, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (h_misc_[kMiscStatus] != kStatusOk) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "strip kernel watchdog fired (status %d, need %d, saw %d)",
+                      h_misc_[kMiscStatus], h_misc_[kMiscStatus + 1], h_misc_[kMiscStatus + 2]);
+        set_last_error(buf);
+        return ANYSEQ_ERR_KERNEL_TIMEOUT;
+    }
+    float ms = 0.f;
+    ANYSEQ_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    if (out) {
+        out->row_best = h_misc_[kMiscOut + 3];
+        out->row_best_j = h_misc_[kMiscOut + 4];
+        out->col_best = h_misc_[kMiscOut + 5];
+        out->col_best_i = h_misc_[kMiscOut + 6];
+        out->corner = h_misc_[kMiscOut + 7];
+        out->local_best = h_misc_[kMiscBest];
+        out->kernel_ms = ms;
+        out->kernel_launches = launches;
+    }
+    return ANYSEQ_OK;
+}
+
+int Engine::score_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                       anyseq_result* out)
+{
+    if (m < 0 || n < 0 || !out || (m > 0 && !q) || (n > 0 && !s)) { set_last_error("bad arguments"); return ANYSEQ_ERR_BAD_ARG; }
+    if (m == 0 || n == 0) { empty_result(sc, m, n, out); return ANYSEQ_OK; }
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
+    if (seq_q_.ensure((size_t)m + 64) || seq_s_.ensure((size_t)n + 64)) return ANYSEQ_ERR_NO_DEVICE;
+    // sequence_to_device: src/mapping_acc.impala:125-131
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_q_.ptr, q, (size_t)m, cudaMemcpyHostToDevice, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_s_.ptr, s, (size_t)n, cudaMemcpyHostToDevice, stream_));
+    return score_device(sc, seq_q_.as<uint8_t>(), m, seq_s_.as<uint8_t>(), n, out);
+}
+
+}  // namespace anyseq

@@ -1,0 +1,115 @@
+// engine.cuh -- host-side engine: workspace, job construction, launches.
+#pragma once
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/anyseq.h"
+
+namespace anyseq {
+
+// grow-only device allocation
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (ptr) ANYSEQ_CUDA_CHECK(cudaFree(ptr));
+        ptr = nullptr;
+        bytes = 0;
+        size_t cap = need + need / 8 + 256;
+        ANYSEQ_CUDA_CHECK(cudaMalloc(&ptr, cap));
+        bytes = cap;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+struct Tuning {
+    int cols_per_lane = 0;   // K, 0 = auto
+    int band_rows = 0;       // 0 = auto
+    int blocks_per_sm = 0;   // 0 = occupancy maximum
+    int watchdog_ms = 20000;
+};
+
+// word layout of the small device "misc" block
+enum MiscWord : int {
+    kMiscStatus = 0,     // 4 words
+    kMiscBest = 4,       // local running maximum
+    kMiscOut = 8,        // 8 words: finish kernel output
+    kMiscWords = 32
+};
+
+struct Inbox {            // left-border mailbox of a rank (multi-GPU wavefront)
+    int* base = nullptr;  // [0..63] header (word 0 = progress), then H[rows], E[rows]
+    int rows = 0;
+    bool owned = false;   // false: opened from a peer's IPC handle
+    int* progress() const { return base; }
+    int* H() const { return base + 64; }
+    int* E() const { return base + 64 + ((rows + 63) / 64) * 64; }
+    static size_t bytes_for(int rows) { return sizeof(int) * (64 + 2 * (size_t)((rows + 63) / 64) * 64); }
+};
+
+class Engine {
+public:
+    int init(int device);
+    void destroy();
+
+    int score_device(const anyseq_scoring& sc, const uint8_t* d_q, int m, const uint8_t* d_s, int n,
+                     anyseq_result* out);
+    int score_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                   anyseq_result* out);
+    int score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int m,
+                           const uint8_t* d_s_slice, int col_begin, int col_end, int n_total,
+                           Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out);
+    int align_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                   char* alq, char* als, anyseq_result* out);
+    int score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, const int64_t* d_qoff,
+                           const uint8_t* d_s, const int64_t* d_soff, int64_t npairs,
+                           int32_t* d_scores, anyseq_result* out);
+    int score_batch_host(const anyseq_scoring& sc, const char* q, const int64_t* qoff,
+                         const char* s, const int64_t* soff, int64_t npairs, int32_t* scores,
+                         anyseq_result* out);
+    int measure_int_peak(int kind, double* ops_per_s, float* sm_mhz);
+
+    int inbox_create(int rows, Inbox** out, void* handle64);
+    int inbox_open(const void* handle64, int rows, Inbox** out);
+    int inbox_reset(Inbox* box);
+    void inbox_destroy(Inbox* box);
+
+    Tuning tune;
+    int device = -1;
+    int sm_count = 0;
+    char name[64] = {0};
+    int resident_warps(int K, bool local, bool affine);
+
+private:
+    int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
+                 int* launches);
+    int pick_K(int n) const;
+    int pick_band(int m, int nstrips, int resident) const;
+
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    DeviceBuffer seq_q_, seq_s_, seq_qr_, seq_sr_;
+    DeviceBuffer colH_, colE_, rowH_, rowF_, corner_, progress_, jobs_, misc_;
+    DeviceBuffer colH2_, colE2_;      // second column set (Hirschberg right halves)
+    DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
+    DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
+    int* h_misc_ = nullptr;           // pinned mirror of misc_
+    int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
+    std::recursive_mutex mu_;
+};
+
+void set_last_error(const std::string& s);
+
+}  // namespace anyseq
