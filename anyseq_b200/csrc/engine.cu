@@ -255,6 +255,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ka.njobs = njobs;
     ka.total_items = total;
     ka.sp = sp;
+    ka.one = 1;
     ka.status = misc_.as<int>() + kMiscStatus;
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
     void* args[] = {&ka};

@@ -24,6 +24,8 @@
 // that E and F need one VIADDMNMX each:  E' = max(E + ge, X_left).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace anyseq {
@@ -37,6 +39,7 @@ struct KernelArgs {
     int njobs;
     long long total_items;
     ScoreParams sp;
+    int one;                        // == 1, opaque to the compiler (see imad_add)
     int* status;                    // [0] StatusCode, [1..3] diagnostics
     unsigned long long timeout_ns;  // watchdog for dependency waits
 };
@@ -66,6 +69,27 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+
+// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot fold (one == 1
+// at run time).  The B200 issues IMAD (FMA pipe) and DPX/compare ops (ALU pipe)
+// side by side at 64 lanes/clk/SM each (measured: microbench.cu kind 4), so every
+// add moved here is an ALU slot freed for VIADDMNMX / VIMNMX3.
+__device__ __forceinline__ int imad_add(int a, int one, int b)
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+// d + (q == s ? same : diff): one compare (ALU) and two IMADs, the second one
+// predicated -- no SEL.
+__device__ __forceinline__ int diag_plus_sigma(int qc, int sc, int d, int one, int diff, int same)
+{
+    int dd;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tmad.lo.s32 %0, %3, %4, %5;\n\t@p mad.lo.s32 %0, %3, %4, %6;\n\t}"
+        : "=&r"(dd)
+        : "r"(qc), "r"(sc), "r"(d), "r"(one), "r"(diff), "r"(same));
+    return dd;
 }
 
 // Wait until *flag >= need.  Executed by all lanes of a warp (same address:
@@ -119,11 +143,17 @@ __device__ __forceinline__ void load_row_ints(const int* __restrict__ p, int (&d
 // don't-care values (dependencies only run left->right, so they never reach a
 // valid cell), the edge column is picked out for the output, and the local
 // maximum is masked.
+//
+// Instruction budget per cell (SASS, checked with cuobjdump):
+//   Gotoh : ISETP, VIADDMNMX (E), VIADDMNMX (F), VIMNMX3[.RELU]   -> 4 ALU
+//           IMAD, @p IMAD (diag + sigma), IMAD (X = H + open)     -> 3 FMA
+//   linear: ISETP, VIMNMX, VIADDMNMX[.RELU]                       -> 3 ALU
+//           IMAD, @p IMAD                                         -> 2 FMA
 template <bool LOCAL, bool AFFINE, int K, bool PARTIAL>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
-                                             const ScoreParams& sp, int2* __restrict__ s_in,
-                                             int2* __restrict__ s_out, uint8_t* __restrict__ s_q,
-                                             const int lane, int* status,
+                                             const ScoreParams& sp, const int one,
+                                             int2* __restrict__ s_in, int2* __restrict__ s_out,
+                                             uint8_t* __restrict__ s_q, const int lane, int* status,
                                              const unsigned long long timeout_ns)
 {
     constexpr int SW = kWarp * K;
@@ -136,22 +166,23 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     const int ge = sp.gap_extend;
     const int same_o = sp.same - go, diff_o = sp.diff - go;
 
-    // left border source
+    // left border source (rows of this band)
     const int* linH;
     const int* linE;
     const int* lflag;
     bool lsys = false;
     if (strip == 0) {
-        linH = J.inH ? J.inH : J.colH;
-        linE = J.inH ? J.inE : J.colE;
+        linH = (J.inH ? J.inH : J.colH) + i0;
+        linE = AFFINE ? (J.inH ? J.inE : J.colE) + i0 : nullptr;
         lflag = J.in_progress;
         lsys = true;
     } else {
-        linH = J.colH;
-        linE = J.colE;
+        linH = J.colH + i0;
+        linE = AFFINE ? J.colE + i0 : nullptr;
         lflag = J.progress + (strip - 1);
     }
     const bool mirror = last_strip && (J.outH != nullptr);
+    const uint8_t* qrow = J.q + i0;
 
     // the band above must be complete (its bottom border is our top border)
     if (band > 0) {
@@ -209,6 +240,60 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         }
     };
 
+    // one anti-diagonal step; GUARD = some lanes may be outside [0, hb)
+    auto step = [&](auto guard_tag, const int t) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
+        int xl = __shfl_up_sync(kFull, hr, 1);
+        int el = 0;
+        if constexpr (AFFINE) el = __shfl_up_sync(kFull, er, 1);
+        const int2 bnd = s_in[t & 31];
+        if (lane == 0) { xl = bnd.x; el = bnd.y; }
+        const int i = t - lane;
+        if (!GUARD || (unsigned)i < (unsigned)hb) {
+            const int qc = s_q[i & 63];
+            int d = dcarry;
+            dcarry = xl;
+            int xleft = xl;
+            int e = el;
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+                const int up = X[c];
+                int h;
+                if constexpr (AFFINE) {
+                    const int dd = diag_plus_sigma(qc, sc[c], d, one, diff_o, same_o);
+                    e = __viaddmax_s32(e, ge, xleft);
+                    const int f = __viaddmax_s32(F[c], ge, up);
+                    h = LOCAL ? __vimax3_s32_relu(dd, e, f) : __vimax3_s32(dd, e, f);
+                    F[c] = f;
+                } else {
+                    const int dd = diag_plus_sigma(qc, sc[c], d, one, sp.diff, sp.same);
+                    const int tmax = max(xleft, up);
+                    h = LOCAL ? __viaddmax_s32_relu(tmax, ge, dd) : __viaddmax_s32(tmax, ge, dd);
+                }
+                if constexpr (LOCAL) {
+                    if (!PARTIAL || c < nvalid) best = max(best, h);
+                }
+                const int x = AFFINE ? imad_add(h, one, go) : h;
+                d = up;
+                X[c] = x;
+                xleft = x;
+            }
+            hr = xleft;
+            er = e;
+            if constexpr (PARTIAL) {
+                if (lane == outlane) {
+                    int hs = X[0];
+#pragma unroll
+                    for (int c = 1; c < K; ++c)
+                        if (c == outc) hs = X[c];
+                    s_out[i & 63] = make_int2(hs, 0);
+                }
+            } else {
+                if (lane == 31) s_out[i & 63] = make_int2(hr, er);
+            }
+        }
+    };
+
     for (int tb = 0; tb < T; tb += 32) {
         __syncwarp();
         // (1) publish the edge rows the out lane finished so far
@@ -232,70 +317,24 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                     if (!wait_rows(lflag, i0 + min(tb + 32, hb), lsys, status, timeout_ns)) return false;
                 }
                 if (r < hb) {
-                    v.x = __ldcg(linH + i0 + r) + go;
-                    if constexpr (AFFINE) v.y = __ldcg(linE + i0 + r);
-                    qv = J.q[i0 + r];
+                    v.x = __ldcg(linH + r) + go;
+                    if constexpr (AFFINE) v.y = __ldcg(linE + r);
+                    qv = qrow[r];
                 }
             }
             s_in[lane] = v;
             s_q[r & 63] = qv;
             __syncwarp();
         }
-        // (3) 32 anti-diagonal steps
-        const int tend = min(tb + 32, T);
+        // (3) 32 anti-diagonal steps; batches in which every lane is inside the
+        //     band run the unguarded body
+        if (tb >= 31 && tb + 32 <= hb) {
 #pragma unroll 1
-        for (int t = tb; t < tend; ++t) {
-            int xl = __shfl_up_sync(kFull, hr, 1);
-            int el = 0;
-            if constexpr (AFFINE) el = __shfl_up_sync(kFull, er, 1);
-            const int2 bnd = s_in[t & 31];
-            if (lane == 0) { xl = bnd.x; el = bnd.y; }
-            const int i = t - lane;
-            if (i >= 0 && i < hb) {
-                const int qc = s_q[i & 63];
-                int d = dcarry;
-                dcarry = xl;
-                int xleft = xl;
-                int e = el;
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    const int up = X[c];
-                    int h;
-                    if constexpr (AFFINE) {
-                        const int sub = (qc == sc[c]) ? same_o : diff_o;
-                        e = __viaddmax_s32(e, ge, xleft);
-                        const int f = __viaddmax_s32(F[c], ge, up);
-                        const int dd = d + sub;
-                        h = LOCAL ? __vimax3_s32_relu(dd, e, f) : __vimax3_s32(dd, e, f);
-                        F[c] = f;
-                    } else {
-                        const int sub = (qc == sc[c]) ? sp.same : sp.diff;
-                        const int dd = d + sub;
-                        const int tmax = max(xleft, up);
-                        h = LOCAL ? __viaddmax_s32_relu(tmax, ge, dd) : __viaddmax_s32(tmax, ge, dd);
-                    }
-                    if constexpr (LOCAL) {
-                        if (!PARTIAL || c < nvalid) best = max(best, h);
-                    }
-                    const int x = h + go;
-                    d = up;
-                    X[c] = x;
-                    xleft = x;
-                }
-                hr = xleft;
-                er = e;
-                if constexpr (PARTIAL) {
-                    if (lane == outlane) {
-                        int hs = X[0];
-#pragma unroll
-                        for (int c = 1; c < K; ++c)
-                            if (c == outc) hs = X[c];
-                        s_out[i & 63] = make_int2(hs, 0);
-                    }
-                } else {
-                    if (lane == 31) s_out[i & 63] = make_int2(hr, er);
-                }
-            }
+            for (int t = tb; t < tb + 32; ++t) step(std::false_type{}, t);
+        } else {
+            const int tend = min(tb + 32, T);
+#pragma unroll 1
+            for (int t = tb; t < tend; ++t) step(std::true_type{}, t);
         }
     }
 
@@ -333,8 +372,12 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     return true;
 }
 
+// registers per thread are capped so that 4 CTAs (16 warps, 4 per scheduler)
+// fit on an SM for every K: the recurrence has a 3-deep dependent chain per cell
+// and needs that many warps to keep the ALU pipe busy.
 template <bool LOCAL, bool AFFINE, int K>
-__global__ void __launch_bounds__(kThreads) strip_kernel(const KernelArgs a)
+__global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6)))
+strip_kernel(const KernelArgs a)
 {
     __shared__ int2 s_in[kWarpsPerBlock][32];
     __shared__ int2 s_out[kWarpsPerBlock][64];
@@ -349,18 +392,20 @@ __global__ void __launch_bounds__(kThreads) strip_kernel(const KernelArgs a)
     for (long long item = (long long)blockIdx.x * kWarpsPerBlock + warp; item < a.total_items;
          item += nwarps) {
         while (jcur + 1 < a.njobs && item >= a.jobs[jcur + 1].item_begin) ++jcur;
-        const Job J = a.jobs[jcur];
+        const Job& J = a.jobs[jcur];
         const long long loc = item - J.item_begin;
         const int band = (int)(loc / J.nstrips);
         const int strip = (int)(loc % J.nstrips);
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)
-            ok = process_item<LOCAL, AFFINE, K, true>(J, band, strip, a.sp, s_in[warp], s_out[warp],
-                                                      s_q[warp], lane, a.status, a.timeout_ns);
+            ok = process_item<LOCAL, AFFINE, K, true>(J, band, strip, a.sp, a.one, s_in[warp],
+                                                      s_out[warp], s_q[warp], lane, a.status,
+                                                      a.timeout_ns);
         else
-            ok = process_item<LOCAL, AFFINE, K, false>(J, band, strip, a.sp, s_in[warp], s_out[warp],
-                                                       s_q[warp], lane, a.status, a.timeout_ns);
+            ok = process_item<LOCAL, AFFINE, K, false>(J, band, strip, a.sp, a.one, s_in[warp],
+                                                       s_out[warp], s_q[warp], lane, a.status,
+                                                       a.timeout_ns);
         if (!ok) return;
     }
 }
