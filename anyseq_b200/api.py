@@ -142,6 +142,13 @@ class Aligner:
         return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches,
                                oq[:n].tobytes(), os_[:n].tobytes())
 
+    def last_splits(self):
+        """split rows of the last align() (slot -1 first), src/traceback_lintime.impala:9-42"""
+        n = self._lib.anyseq_last_splits(self._ctx, None, 0)
+        buf = (C.c_int32 * max(n, 1))()
+        self._lib.anyseq_last_splits(self._ctx, buf, n)
+        return list(buf[:n])
+
     # -- batches of independent pairs --------------------------------------
     def score_batch(self, mode, queries, q_off, subjects, s_off, scoring: ScoringScheme = REFERENCE_SCORING):
         q, s = as_u8(queries), as_u8(subjects)

@@ -1,0 +1,181 @@
+// align_main.cpp -- the `align` demo/benchmark CLI on top of the C ABI.
+//
+// Same surface as the reference's host program (src/main.cpp:124-235):
+//     align [-o <file>] -i <query file> <subject file>
+//     align [-o <file>] -r [<min length> [<max length>]]
+// prints the input description, the sequence lengths and six lines
+// "testing <name> <ms> ms" (three score-only calls, three linear-space
+// traceback calls) -- results are computed and discarded like the reference
+// does, unless -p/--print is given (an addition: print_alignment of each
+// traceback).  -o is documented by the reference's README (README.md:41,46) but
+// disabled in its source; it is enabled here.  Random inputs follow the
+// reference recipe (default-seeded std::mt19937_64, query first).
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "anyseq.h"
+#include "alignment_io.h"
+#include "sequence_io.h"
+
+namespace {
+
+using ScoreFn = score_t (*)(const char*, int, const char*, int);
+using AlignFn = score_t (*)(const char*, int, const char*, int, char*, char*);
+
+long long elapsed_ms(std::chrono::steady_clock::time_point t0)
+{
+    return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void time_score(const char* name, ScoreFn fn, const std::string& q, const std::string& s, std::ostream& os)
+{
+    os << "testing " << name << std::flush;
+    const auto t0 = std::chrono::steady_clock::now();
+    volatile score_t r = fn(q.data(), static_cast<int>(q.size()), s.data(), static_cast<int>(s.size()));
+    (void)r;
+    os << " " << elapsed_ms(t0) << " ms" << std::endl;
+}
+
+void time_align(const char* name, AlignFn fn, const std::string& q, const std::string& s, std::string& aq,
+                std::string& as, std::ostream& os, bool print)
+{
+    os << "testing " << name << std::flush;
+    const auto t0 = std::chrono::steady_clock::now();
+    volatile score_t r = fn(q.data(), static_cast<int>(q.size()), s.data(), static_cast<int>(s.size()), &aq[0], &as[0]);
+    os << " " << elapsed_ms(t0) << " ms" << std::endl;
+    if (print) anyseq_host::print_alignment(os, r, aq, as);
+}
+
+void run_all(const std::string& q, const std::string& s, std::ostream& os, bool print)
+{
+    time_score("global score", global_alignment_score, q, s, os);
+    time_score("semiglobal score", semiglobal_alignment_score, q, s, os);
+    time_score("local score", local_alignment_score, q, s, os);
+    std::string aq(q.size() + s.size(), ' '), as(q.size() + s.size(), ' ');
+    time_align("global alignment", construct_global_alignment, q, s, aq, as, os, print);
+    time_align("semiglobal alignment", construct_semiglobal_alignment, q, s, aq, as, os, print);
+    time_align("local alignment", construct_local_alignment, q, s, aq, as, os, print);
+}
+
+template <class Rng>
+std::string random_dna(std::int64_t lo, std::int64_t hi, Rng& rng)
+{
+    // libstdc++ distributions instantiated for the same result types as the
+    // reference (size_t for the length, char for the symbol): the produced
+    // bytes depend on both
+    static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+    std::uniform_int_distribution<std::size_t> len(static_cast<std::size_t>(lo), static_cast<std::size_t>(hi));
+    std::string out(len(rng), 'A');
+    std::uniform_int_distribution<char> sym(0, 3);
+    for (char& c : out) {
+        const char v = sym(rng);
+        c = (v >= 0 && v < 4) ? alphabet[static_cast<int>(v)] : '_';
+    }
+    return out;
+}
+
+void usage(const char* argv0)
+{
+    std::cout << "SYNOPSIS\n"
+              << "        " << argv0 << " [-o <file>] [-p] (-i|--in) <query file> <subject file>\n"
+              << "        " << argv0 << " [-o <file>] [-p] (-r|--rand) [<min len>] [<max len>]\n\n"
+              << "OPTIONS\n"
+              << "        -i, --in    read sequences from input files (first record of each)\n"
+              << "        -r, --rand  generate random input sequences\n"
+              << "        -o, --out   write results to file\n"
+              << "        -p, --print print the alignments (print_alignment format)\n";
+}
+
+bool parse_int(const std::string& a, std::int64_t* v)
+{
+    if (a.empty()) return false;
+    char* end = nullptr;
+    const long long x = std::strtoll(a.c_str(), &end, 10);
+    if (*end != '\0') return false;
+    *v = x;
+    return true;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+    enum class Input { none, file, random } input = Input::none;
+    std::string query, subject, outfile;
+    std::int64_t minlen = 256, maxlen = 1024;     // reference defaults (src/main.cpp:134-135)
+    bool print = false, bad = false, want_out = false;
+    std::vector<std::string> unknown;
+
+    for (int k = 1; k < argc; ++k) {
+        const std::string a = argv[k];
+        if ((a == "-o" || a == "--out")) {
+            want_out = true;
+            if (k + 1 < argc) outfile = argv[++k]; else bad = true;
+        } else if (a == "-p" || a == "--print") {
+            print = true;
+        } else if ((a == "-i" || a == "--in") && input == Input::none) {
+            input = Input::file;
+            if (k + 2 < argc) { query = argv[++k]; subject = argv[++k]; } else bad = true;
+        } else if ((a == "-r" || a == "--rand") && input == Input::none) {
+            input = Input::random;
+            std::int64_t v;
+            if (k + 1 < argc && parse_int(argv[k + 1], &v)) { minlen = v; ++k; }
+            if (k + 1 < argc && parse_int(argv[k + 1], &v)) { maxlen = v; ++k; }
+        } else {
+            unknown.push_back(a);
+        }
+    }
+    if (bad || input == Input::none || !unknown.empty()) {
+        if (!unknown.empty()) {
+            std::cout << "Unknown command line arguments:\n";
+            for (const auto& a : unknown) std::cout << "'" << a << "'\n";
+            std::cout << '\n';
+        }
+        usage(argv[0]);
+        return 0;                                  // the reference exits 0 here (src/main.cpp:166-174)
+    }
+
+    if (input == Input::file) {
+        std::cout << "input sequences: " << query << ", " << subject << std::endl;
+        try {
+            auto qr = anyseq_host::make_sequence_reader(query);
+            if (qr->has_next()) query = qr->next().data;
+            auto sr = anyseq_host::make_sequence_reader(subject);
+            if (sr->has_next()) subject = sr->next().data;
+        } catch (std::exception& e) {
+            // the reference prints the message and goes on with whatever the
+            // variables hold (quirk Q9); aligning file names is never intended,
+            // so this build stops instead
+            std::cerr << e.what() << std::endl;
+            return 1;
+        }
+    } else {
+        if (minlen < 1 || maxlen < 1) {
+            std::cerr << "String lenghts must be greater than zero!" << std::endl;
+            return 1;
+        }
+        if (maxlen < minlen) std::swap(minlen, maxlen);
+        std::cout << "random strings with length from [" << minlen << "," << maxlen << "]\n";
+        std::mt19937_64 rng;
+        query = random_dna(minlen, maxlen, rng);
+        subject = random_dna(minlen, maxlen, rng);
+    }
+    std::cout << "sequence lengths: " << query.size() << ", " << subject.size() << std::endl;
+
+    if (want_out) {
+        if (outfile.empty()) { std::cerr << "No output file name given!" << std::endl; return 1; }
+        std::ofstream os(outfile);
+        if (!os.good()) { std::cerr << "Unable to open output file!" << std::endl; return 1; }
+        run_all(query, subject, os, print);
+    } else {
+        run_all(query, subject, std::cout, print);
+    }
+    return 0;
+}

@@ -165,6 +165,7 @@ int Engine::init(int dev)
     if ((env = std::getenv("ANYSEQ_BAND"))) tune.band_rows = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_BLOCKS_PER_SM"))) tune.blocks_per_sm = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_WATCHDOG_MS"))) tune.watchdog_ms = std::atoi(env);
+    if ((env = std::getenv("ANYSEQ_ALIGN_SCORE"))) tune.align_with_score = std::atoi(env) != 0;
     return ANYSEQ_OK;
 }
 
@@ -197,26 +198,30 @@ int Engine::pick_K(int n) const
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
-    if (n >= (1 << 21)) return 32;
-    if (n >= (1 << 18)) return 16;
-    if (n >= (1 << 15)) return 8;
+    // widest strips (least per-step overhead) that still give every resident
+    // warp its own strip: ~2400 warps at K=32, ~3000 at K=16, ~3600 at K=8
+    if (n >= 2400 * 1024) return 32;
+    if (n >= 3000 * 512) return 16;
+    if (n >= 3600 * 256) return 8;
     return 4;
 }
 
-// Band height: enough (band, strip) items in flight to occupy every resident
-// warp (the wavefront over items holds about nstrips + band_h/lag of them) and
-// enough items per warp for balance.
+// Band height.  Items are taken in index order by a window of `resident` warps,
+// i.e. `resident` consecutive strips of one band, each `lag` steps behind its
+// left neighbour (32 steps lane skew + the 32-row publish/fetch granularity).
+// All of them overlap only if a band is at least lag * window steps long;
+// bands are then equalised.
 int Engine::pick_band(int m, int nstrips, int resident) const
 {
     if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
     const long long lag = 128;
-    long long need = std::max(0, resident - nstrips) * lag;
-    long long nb_bal = (64LL * resident + nstrips - 1) / nstrips;
-    long long bh_bal = std::max<long long>(m / std::max<long long>(nb_bal, 1), 2048);
-    long long bh = std::max(need, std::min<long long>(bh_bal, 1 << 16));
-    bh = std::min<long long>(bh, m);
+    const long long window = std::max(1, std::min(resident, nstrips));
+    long long target = std::max<long long>(lag * window, 4096);
+    if (target >= m) return std::max(32, (m + 31) / 32 * 32);
+    const long long nbands = (m + target - 1) / target;
+    long long bh = (m + nbands - 1) / nbands;
     bh = (bh + 31) / 32 * 32;
-    return (int)std::max<long long>(bh, 32);
+    return (int)bh;
 }
 
 // Launch init + strip kernels for a job list that is already in host memory.
@@ -264,7 +269,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     return ANYSEQ_OK;
 }
 
-static int make_params(const anyseq_scoring& sc, ScoreParams* sp, bool* affine)
+int make_score_params(const anyseq_scoring& sc, ScoreParams* sp, bool* affine)
 {
     if (sc.mode < 0 || sc.mode > 2 || sc.gap_init > 0 || sc.gap_extend > 0) {
         set_last_error("bad scoring scheme (mode in 0..2, gap costs must be <= 0)");
@@ -319,14 +324,13 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
     ScoreParams sp;
     bool affine;
-    int rc = make_params(sc, &sp, &affine);
+    int rc = make_score_params(sc, &sp, &affine);
     if (rc) return rc;
     const int w = col_end - col_begin;
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
     const bool local = sc.mode == ANYSEQ_LOCAL;
     const int K = pick_K(w);
     const int SW = kWarp * K;
-    if (inbox && (col_begin % SW) != 0) { set_last_error("strip boundary must be a multiple of the strip width"); return ANYSEQ_ERR_BAD_ARG; }
     const int nstrips = (w + SW - 1) / SW;
     const int resident = resident_warps(K, local, affine);
     const int band_h = pick_band(m, nstrips, resident);

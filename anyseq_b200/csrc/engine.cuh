@@ -39,6 +39,7 @@ struct Tuning {
     int band_rows = 0;       // 0 = auto
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
+    bool align_with_score = true;   // anyseq_align also computes the optimal score (one more m*n pass)
 };
 
 // word layout of the small device "misc" block
@@ -87,6 +88,7 @@ public:
     void inbox_destroy(Inbox* box);
 
     Tuning tune;
+    const std::vector<int>& last_splits() const { return last_splits_; }
     int device = -1;
     int sm_count = 0;
     char name[64] = {0};
@@ -106,10 +108,12 @@ private:
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
     int* h_misc_ = nullptr;           // pinned mirror of misc_
+    std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
     std::recursive_mutex mu_;
 };
 
 void set_last_error(const std::string& s);
+int make_score_params(const anyseq_scoring& sc, ScoreParams* sp, bool* affine);
 
 }  // namespace anyseq

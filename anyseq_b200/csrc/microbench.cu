@@ -9,8 +9,13 @@
 //   kind 2  the 7-op affine-gap cell mix           ISETP SEL IADD 2xVIADDMNMX VIMNMX3 IADD
 //   kind 3  IMAD only                              (FMA pipe)
 //   kind 4  kind 0 and kind 3 interleaved 1:1      (do the pipes dual-issue?)
+//   kind 5  the strip kernel's own Gotoh cell      ISETP 2xVIADDMNMX VIMNMX3 | 3x IMAD
+//   kind 6  the strip kernel's own linear cell     ISETP VIMNMX VIADDMNMX    | 2x IMAD
+//           (kinds 5/6 return CELLS per second: the cell-update peak of the mix
+//            the kernel really executes, both pipes busy)
 // The result is lane-operations per second over the whole chip.
 #include "engine.cuh"
+#include "strip_kernel.cuh"
 
 namespace anyseq {
 
@@ -55,6 +60,17 @@ __global__ void __launch_bounds__(256) int_peak_kernel(const int* __restrict__ i
                     const int dd = b[k] + sub;
                     const int h = __vimax3_s32(dd, e, f);
                     a[k] = e; d[k] = f; b[k] = h + p3;
+                } else if constexpr (KIND == 5) {
+                    const int dd = diag_plus_sigma(c[k], p1, b[k], p3, p0, p1);
+                    const int e = __viaddmax_s32(a[k], p2, b[k]);
+                    const int f = __viaddmax_s32(d[k], p2, c[k]);
+                    const int h = __vimax3_s32(dd, e, f);
+                    a[k] = e; d[k] = f; c[k] = b[k]; b[k] = imad_add(h, p3, p2);
+                } else if constexpr (KIND == 6) {
+                    const int dd = diag_plus_sigma(c[k], p1, a[k], p3, p0, p1);
+                    const int t = max(b[k], d[k]);
+                    const int h = __viaddmax_s32(t, p2, dd);
+                    c[k] = a[k]; a[k] = d[k]; d[k] = b[k]; b[k] = h;
                 } else if constexpr (KIND == 3) {
                     a[k] = a[k] * p0 + b[k];
                     b[k] = b[k] * p1 + a[k];
@@ -80,6 +96,8 @@ static int ops_per_inner(int kind)
         case 1: return 5;   // counted as the algorithmic 5 (the xor feeding d is bookkeeping)
         case 2: return 7;
         case 3: return 2;
+        case 5: return 1;   // cells
+        case 6: return 1;   // cells
         default: return 2;
     }
 }
@@ -88,7 +106,7 @@ int Engine::measure_int_peak(int kind, double* ops_per_s, float* sm_mhz)
 {
     std::lock_guard<std::recursive_mutex> lock(mu_);
     ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
-    if (kind < 0 || kind > 4) return ANYSEQ_ERR_BAD_ARG;
+    if (kind < 0 || kind > 6) return ANYSEQ_ERR_BAD_ARG;
     const int blocks = sm_count * 8, threads = 256;
     const int iters = 20000;
     if (aux_.ensure(sizeof(int) * 1024 + sizeof(int) * (size_t)blocks * threads + sizeof(long long) * blocks + 64))
@@ -105,6 +123,8 @@ int Engine::measure_int_peak(int kind, double* ops_per_s, float* sm_mhz)
             case 1: int_peak_kernel<1><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, 2, -1, -1, 0, d_clk); break;
             case 2: int_peak_kernel<2><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, 2, -1, -1, -3, d_clk); break;
             case 3: int_peak_kernel<3><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, 3, 5, 0, 0, d_clk); break;
+            case 5: int_peak_kernel<5><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, -1, 2, -1, 1, d_clk); break;
+            case 6: int_peak_kernel<6><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, -1, 2, -1, 1, d_clk); break;
             default: int_peak_kernel<4><<<blocks, threads, 0, stream_>>>(d_in, d_out, n, -1, 3, 0, 0, d_clk); break;
         }
     };

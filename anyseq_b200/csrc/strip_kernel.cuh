@@ -255,6 +255,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             dcarry = xl;
             int xleft = xl;
             int e = el;
+            int es = 0;   // PARTIAL: E of the edge column
 #pragma unroll
             for (int c = 0; c < K; ++c) {
                 const int up = X[c];
@@ -262,6 +263,9 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 if constexpr (AFFINE) {
                     const int dd = diag_plus_sigma(qc, sc[c], d, one, diff_o, same_o);
                     e = __viaddmax_s32(e, ge, xleft);
+                    if constexpr (PARTIAL) {
+                        if (c == outc) es = e;
+                    }
                     const int f = __viaddmax_s32(F[c], ge, up);
                     h = LOCAL ? __vimax3_s32_relu(dd, e, f) : __vimax3_s32(dd, e, f);
                     F[c] = f;
@@ -286,7 +290,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #pragma unroll
                     for (int c = 1; c < K; ++c)
                         if (c == outc) hs = X[c];
-                    s_out[i & 63] = make_int2(hs, 0);
+                    s_out[i & 63] = make_int2(hs, es);
                 }
             } else {
                 if (lane == 31) s_out[i & 63] = make_int2(hr, er);

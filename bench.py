@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the DP-relaxation hot path on the BASELINE.json workload.
+
+Workload (BASELINE.json configs[1] / configs[4]): ecoli x sboydii, semi-global,
+affine (Gotoh) gaps (same=2, diff=-1, gapInit=-2, gapExtend=-1), score-only,
+~4.64 Mbp x 4.6 Mbp.  The bundled genomes are missing from the reference mount,
+so seeded synthetic stand-ins are used (anyseq_b200/workloads.py) unless
+sequences/ecoli.fna and sequences/sboydii.fna exist.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" = one complete score-only alignment
+of the pair.  N > 1 (torchrun): the pair is split into N column strips, one per
+GPU, chained by the strip-boundary column over NVLink (strong scaling).
+
+  value     whole-job GCUPS, sequences resident in HBM, device time (CUDA events
+            recorded by the library on the stream it launches on), max over ranks
+  e2e       same metric through the C ABI with HOST buffers (H2D + D2H inside)
+  roofline  integer/DPX issue roofline measured live on this GPU
+  cpu_baseline  the oracle's restated reference CPU path on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCORING = dict(same=2, diff=-1, gap_init=-2, gap_extend=-1)
+MODE = "semiglobal"
+OPS_PER_CELL_AFFINE = 7        # algorithmic 32-bit integer ops per Gotoh cell
+METRIC = "GCUPS (score-only ecoli x sboydii affine)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "250"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clk, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                clk.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v == "Active":
+                    reasons.add(nm)
+        if not clk:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(clk)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_median": float(np.median(pw)), "samples": len(clk)}
+
+
+def cpu_baseline(q, s, sample_rows, sample_cols, threads):
+    """restated reference CPU path (oracle port: 1024x1024 block wavefront, scalar
+    inner loop, Gotoh as defined by the build) on a bounded sample of the workload"""
+    from oracle import oracle as O
+    qs, ss = q[:sample_rows], s[:sample_cols]
+    t0 = time.perf_counter()
+    sc = O.score_affine(MODE, qs, ss, SCORING["same"], SCORING["diff"], SCORING["gap_init"],
+                        SCORING["gap_extend"], threads=threads)
+    dt = time.perf_counter() - t0
+    return len(qs) * len(ss) / dt / 1e9, dt, sc[0]
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host
+    cores.  AnyDSL/Impala cannot be built here, so this is the oracle's
+    restatement of iteration_cpu/scoring_cpu (kind "port") with all host threads."""
+    if rank != 0:
+        return 0
+    from anyseq_b200 import workloads as W
+    q, s, desc = W.whole_genome_pair(args.scale)
+    threads = os.cpu_count() or 1
+    side = int(args.cpu_sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        g, dt, _ = cpu_baseline(q, s, side, side, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = side * side / (ms * 1e-3) / 1e9
+    sample = f"first {side} x {side} cells of the workload per step ({side*side:.3g} cells), all {threads} host threads"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc + "; semiglobal affine (2,-1,-2,-1) score-only", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
+    ap.add_argument("--cpu-sample", type=int, default=40000, help="side of the CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import anyseq_b200 as A
+    from anyseq_b200 import workloads as W
+    from anyseq_b200.multigpu import StripWavefront, column_slices
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (anyseq_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    q, s, desc = W.whole_genome_pair(args.scale)
+    m, n = len(q), len(s)
+    cells = float(m) * float(n)
+    scoring = A.affine_scoring_scheme(**SCORING)
+    al = A.Aligner(local_rank)
+    info = al.device_info()
+
+    slices = column_slices(n, world)
+    c0, c1 = slices[rank]
+    h_q = torch.from_numpy(q).pin_memory()
+    h_s = torch.from_numpy(np.ascontiguousarray(s[c0:c1])).pin_memory()
+    d_q = h_q.cuda()
+    d_s = h_s.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    wave = StripWavefront(al, rank, world, m, dist)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        flush.zero_()
+        wave.reset()
+        torch.cuda.synchronize()
+        part = wave.run(MODE, scoring, d_q.data_ptr(), m, d_s.data_ptr(), c0, c1, n)
+        return part
+
+    # ---- value: inputs resident in HBM -----------------------------------------
+    for _ in range(args.warmup):
+        part = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        part = step_resident()
+        dev_ms += part.kernel_ms
+        launches += part.kernel_launches
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    res = wave.combine(MODE, scoring, part)
+    t = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = t.tolist()
+    ms_per_step = dev_ms_max / args.steps
+    value = cells / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the public API --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def step_e2e():
+            if world == 1:
+                # the reference-facing C ABI call with HOST pointers: H2D of both
+                # sequences, kernels, D2H of the result, all inside the call
+                return al.score(MODE, h_q.numpy(), h_s.numpy(), scoring).score
+            wave.reset()
+            dq = h_q.cuda(non_blocking=True)
+            ds = h_s.cuda(non_blocking=True)
+            torch.cuda.synchronize()
+            p = wave.run(MODE, scoring, dq.data_ptr(), m, ds.data_ptr(), c0, c1, n)
+            return wave.combine(MODE, scoring, p).score
+
+        step_e2e()   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sc_e2e = step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+        e2e = {"value": cells * e2e_steps / dt / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(m + (c1 - c0)) if world > 1 else int(m + n),
+               "d2h_bytes_per_step": 128, "steps": e2e_steps, "score": int(sc_e2e)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline: integer/DPX issue rate measured on this GPU -------------------
+    peak_alu, _ = al.measure_int_peak(0)          # VIADDMNMX/VIMNMX3 only, lane-ops/s
+    peak_mix7, _ = al.measure_int_peak(2)         # the 7-op all-ALU Gotoh mix, lane-ops/s
+    peak_cells_dual, _ = al.measure_int_peak(5)   # the kernel's own 4 ALU + 3 IMAD cell, cells/s
+    achieved_ops = (cells / (ms_per_step * 1e-3)) * OPS_PER_CELL_AFFINE / world   # per GPU
+    roofline = {
+        "bound": "int_alu",
+        "achieved": achieved_ops / 1e12, "peak": peak_alu / 1e12, "unit": "Tlaneop/s (int32, per GPU)",
+        "frac": achieved_ops / peak_alu, "traffic": None,
+        "ops_per_cell": OPS_PER_CELL_AFFINE,
+        "peak_source": "measured live: anyseq_measure_int_peak(kind=0), dependency-free VIADDMNMX/VIMNMX3 loop",
+        "peak_gcups_alu7": peak_alu / OPS_PER_CELL_AFFINE / 1e9,
+        "peak_gcups_mix7_measured": peak_mix7 / OPS_PER_CELL_AFFINE / 1e9,
+        "peak_gcups_dual_pipe_mix": peak_cells_dual / 1e9,
+        "frac_of_dual_pipe_mix": (value / world) / (peak_cells_dual / 1e9),
+        "hbm": {"achieved_gbs": None, "peak_gbs": 6452.8, "note": "boundary traffic only; see profiles/"},
+    }
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        side = int(args.cpu_sample)
+        g, dt, _ = cpu_baseline(q, s, side, side, threads)
+        cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
+               "sample": f"first {side} x {side} cells of the workload ({dt:.1f} s), restated reference CPU path "
+                         f"(1024x1024 block wavefront, scalar inner loop), {threads} threads"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc + "; semiglobal affine (same=2,diff=-1,gapInit=-2,gapExtend=-1) score-only",
+                   "rows": m, "cols": n, "cells_per_step": cells,
+                   "partition": f"{world} column strip(s), boundary column streamed over NVLink" if world > 1 else "1 GPU",
+                   "l2": "L2 flushed (256 MiB memset) before every timed step",
+                   "timing": "CUDA events on the library's launch stream, summed over steps, max over ranks"},
+        "wall_ms_per_step": wall_ms_max / args.steps,
+        "score": int(res.score),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "device": info["name"], "sm_count": info["sm_count"],
+    }
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -123,6 +123,12 @@ int anyseq_align(anyseq_ctx* ctx, const anyseq_scoring* sc,
                  const char* query, int lenq, const char* subject, int lens,
                  char* alQuery, char* alSubject, anyseq_result* out);
 
+/* Split rows chosen by the last anyseq_align / construct_* call of this ctx
+ * (the reference's Splits vector, src/traceback_lintime.impala:9-42): element 0
+ * is slot -1 (= 0), then one entry per 128-column block.  Returns the number of
+ * entries (writes at most cap). */
+int anyseq_last_splits(anyseq_ctx* ctx, int32_t* out, int cap);
+
 /* Derived view of an alignment pair: CIGAR string (=/X/I/D run-length, I = gap
  * in the query ('_' in alQuery), D = gap in the subject), skipping blank
  * columns.  Returns the length written (excluding the NUL) or -needed if cap is
@@ -176,7 +182,8 @@ int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* p
  * roofline denominator): runs dependency-free loops of the named
  * mix and returns 32-bit lane-operations per second. kind: 0 = VIMNMX/VIADDMNMX
  * only (ALU pipe), 1 = the 5-op linear cell mix, 2 = the 7-op affine cell mix,
- * 3 = IMAD only (FMA pipe), 4 = ALU+IMAD interleaved. */
+ * 3 = IMAD only (FMA pipe), 4 = ALU+IMAD interleaved; 5 / 6 = the strip kernel's own
+ * Gotoh / linear cell instruction sequence (both pipes), returned as CELLS per second. */
 int anyseq_measure_int_peak(anyseq_ctx* ctx, int kind, double* ops_per_s, float* sm_mhz_est);
 
 /* Device properties the bench reports. */

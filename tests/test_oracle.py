@@ -1,0 +1,149 @@
+"""CPU tests of the parity oracle (no GPU): the restated reference CPU path against
+the known answers of SURVEY.md Appendix C, against independent textbook DPs, and
+against the frozen golden fixtures."""
+import hashlib
+
+import numpy as np
+import pytest
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+MODES = ("global", "semiglobal", "local")
+
+
+def _rand(rng, n):
+    return ACGT[rng.integers(0, 4, n)]
+
+
+def test_reference_rng_inputs(oracle, golden):
+    """inputs of `align -r ...` regenerated with the reference's recipe (src/main.cpp:90-120,207-209)"""
+    for (lo, hi), key in (((256, 1024), "align -r"), ((10000, 1024), "align -r 10000"), ((10000, 10000), "align -r 10000 10000")):
+        g = golden["appendix_c"][key]
+        q, s = oracle.reference_random_pair(lo, hi)
+        assert (len(q), len(s)) == (g["m"], g["n"])
+        assert "%016x" % oracle.fnv1a64(q) == g["fnv_q"]
+        assert "%016x" % oracle.fnv1a64(s) == g["fnv_s"]
+        assert bytes(q[:16]) == b"CGTACCAGCCGAGGTC"
+
+
+@pytest.mark.parametrize("key,lo,hi", [("align -r", 256, 1024), ("align -r 10000", 10000, 1024),
+                                       ("align -r 10000 10000", 10000, 10000)])
+def test_appendix_c_scores(oracle, golden, key, lo, hi):
+    q, s = oracle.reference_random_pair(lo, hi)
+    want = golden["appendix_c"][key]["scores"]
+    assert [oracle.score_linear(m, q, s)[0] for m in MODES] == want
+    assert [oracle.textbook_linear(m, q, s) for m in MODES] == want
+
+
+def test_appendix_c_traceback(oracle, golden):
+    g = golden["appendix_c"]["align -r"]
+    q, s = oracle.reference_random_pair(256, 1024)
+    for k, mode in enumerate(MODES):
+        ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s)
+        assert ret == g["legacy_return"][k]                       # quirk Q1
+        assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == g["sha"][mode]
+        assert sum(1 for a, b in zip(aq, as_) if not (a == 32 and b == 32)) == g["nonblank"][mode]
+        assert oracle.column_score(aq, as_) == g["column_score"][mode]
+        if mode == "global":
+            assert sp.tolist() == g["splits_global"]
+
+
+def test_semiglobal_end_cell(oracle):
+    q, s = oracle.reference_random_pair(256, 1024)
+    assert oracle.score_linear("semiglobal", q, s) == (659, 860, 911)
+    assert oracle.score_linear("local", q, s) == (659, 860, 911)
+
+
+def test_restatement_equals_textbook_random(oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        m, n = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        q, s = _rand(rng, m), _rand(rng, n)
+        same, diff, gap = int(rng.integers(1, 6)), -int(rng.integers(0, 5)), -int(rng.integers(0, 5))
+        for mode in MODES:
+            assert oracle.score_linear(mode, q, s, same, diff, gap)[0] == oracle.textbook_linear(mode, q, s, same, diff, gap)
+            gi, ge = -int(rng.integers(1, 12)), -int(rng.integers(0, 4))
+            assert oracle.score_affine(mode, q, s, same, diff, gi, ge)[0] == oracle.textbook_affine(mode, q, s, same, diff, gi, ge)
+
+
+def test_scores_do_not_depend_on_blocking(oracle):
+    """any dependency-respecting order gives the same H"""
+    rng = np.random.default_rng(11)
+    q, s = _rand(rng, 700), _rand(rng, 900)
+    for mode in MODES:
+        ref = oracle.score_linear(mode, q, s)[0]
+        for bw, bh in ((1024, 1024), (128, 1280), (64, 64), (100, 37), (7, 5000)):
+            assert oracle.score_linear(mode, q, s, block_w=bw, block_h=bh)[0] == ref
+            assert oracle.score_affine(mode, q, s, block_w=bw, block_h=bh)[0] == oracle.score_affine(mode, q, s)[0]
+        for thr in (1, 2, 4, 8):
+            assert oracle.score_linear(mode, q, s, threads=thr) == oracle.score_linear(mode, q, s, threads=1)
+
+
+def test_affine_with_zero_gap_init_is_linear(oracle):
+    """SURVEY.md A.7 regression: gi = 0 must reproduce the linear recurrence"""
+    rng = np.random.default_rng(3)
+    q, s = _rand(rng, 500), _rand(rng, 450)
+    for mode in MODES:
+        for gap in (-1, -3):
+            assert oracle.score_affine(mode, q, s, 2, -1, 0, gap)[0] == oracle.score_linear(mode, q, s, 2, -1, gap)[0]
+
+
+def test_reduce_max_lowest_index(oracle):
+    """src/utils.impala:30-49: strict '>' everywhere => lowest index of the maximum"""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 63, 64, 65, 129, 1000, 4097):
+        v = rng.integers(-5, 5, n + 1).astype(np.int32)        # element 0 is slot -1
+        sc, ix = oracle.reduce_max(v, -1, n + 1)
+        assert sc == v.max() and ix == int(np.argmax(v)) - 1
+        sc, ix = oracle.reduce_max(v[1:], 0, n)
+        assert sc == v[1:].max() and ix == int(np.argmax(v[1:]))
+
+
+def test_next_pow_2(oracle):
+    assert [oracle.next_pow_2(i) for i in (0, 1, 2, 3, 4, 5, 128, 129, 1000)] == [0, 1, 2, 4, 4, 8, 128, 256, 1024]
+
+
+def _degap(a: bytes) -> bytes:
+    return bytes(c for c in a if c not in (ord(" "), ord("_")))
+
+
+def test_global_traceback_is_optimal_alignment(oracle):
+    """structural invariants: de-gapped rows reproduce the inputs,
+    the column score equals the optimal global score, rows have equal occupancy"""
+    rng = np.random.default_rng(9)
+    for (m, n) in ((50, 65), (300, 200), (129, 128), (1300, 2300), (900, 4100), (3000, 130)):
+        q = _rand(rng, m)
+        s = q.copy()[: min(m, n)]
+        s = np.concatenate([s, _rand(rng, n - len(s))]) if len(s) < n else s
+        s[rng.integers(0, n, n // 10)] = ord("A")
+        ret, aq, as_, sp = oracle.traceback_lintime("global", q, s)
+        assert ret == -m
+        assert _degap(aq) == bytes(q) and _degap(as_) == bytes(s)
+        assert oracle.column_score(aq, as_) == oracle.score_linear("global", q, s)[0]
+        assert all((a == 32) == (b == 32) for a, b in zip(aq, as_))
+        assert sp[0] == 0 and sp[-1] == m and all(sp[i] <= sp[i + 1] for i in range(len(sp) - 1))
+
+
+def test_short_subject_quirk_q4(oracle):
+    """n <= 64: block height 0 => all of s against gaps, none of q (global); nothing otherwise"""
+    q = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)
+    s = np.frombuffer(b"ACGTTGCA", dtype=np.uint8)
+    ret, aq, as_, sp = oracle.traceback_lintime("global", q, s)
+    assert aq[:8] == b"_" * 8 and as_[:8] == bytes(s) and set(aq[8:]) == {32}
+    ret, aq, as_, sp = oracle.traceback_lintime("local", q, s)
+    assert set(aq) == {32} and set(as_) == {32}
+
+
+def test_golden_fixtures(oracle, golden):
+    for c in golden["cases"]:
+        q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
+        for mode in MODES:
+            for key, exp in c["linear"][mode].items():
+                sa, di, ga = map(int, key.split(","))
+                assert list(oracle.score_linear(mode, q, s, sa, di, ga)) == exp, (c["name"], mode, key)
+            for key, exp in c["affine"][mode].items():
+                sa, di, gi, ge = map(int, key.split(","))
+                assert oracle.score_affine(mode, q, s, sa, di, gi, ge)[0] == exp
+            t = c["traceback"][mode]
+            ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s)
+            assert ret == t["ret"] and sp.tolist() == t["splits"]
+            assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == t["sha"]
