@@ -105,6 +105,9 @@ class Aligner:
     def tune(self, cols_per_lane: int = 0, band_rows: int = 0, blocks_per_sm: int = 0, watchdog_ms: int = 0):
         self._check(self._lib.anyseq_ctx_tune(self._ctx, cols_per_lane, band_rows, blocks_per_sm, watchdog_ms))
 
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.anyseq_ctx_set_option(self._ctx, name.encode(), int(value)))
+
     def device_info(self):
         sm, rw = C.c_int(), C.c_int()
         name = C.create_string_buffer(64)

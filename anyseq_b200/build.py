@@ -16,13 +16,14 @@ OUT = os.path.join(_HERE, "_build")
 LIB = os.path.join(OUT, "libanyseq_b200.so")
 CLI = os.path.join(OUT, "align")
 
-LIB_SOURCES = ["engine.cu", "capi.cu", "microbench.cu", "inbox.cu", "traceback.cu", "batch.cu"]
+LIB_SOURCES = ["engine.cu", "capi.cu", "microbench.cu", "inbox.cu", "traceback.cu", "batch.cu",
+               "strip_inst_00.cu", "strip_inst_01.cu", "strip_inst_10.cu", "strip_inst_11.cu"]
 CLI_SOURCES = ["align_main.cpp", "sequence_io.cpp", "alignment_io.cpp"]
-HEADERS = ["common.cuh", "engine.cuh", "strip_kernel.cuh", "sequence_io.h", "alignment_io.h",
+HEADERS = ["common.cuh", "engine.cuh", "strip_kernel.cuh", "strip_inst.inl", "sequence_io.h", "alignment_io.h",
            os.path.join("..", "..", "include", "anyseq.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("ANYSEQ_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -22,7 +22,7 @@ MODES = {"global": GLOBAL, "semiglobal": SEMIGLOBAL, "local": LOCAL}
 EXPORTED_SYMBOLS = [
     "global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
     "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
-    "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune",
+    "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
     "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
@@ -85,6 +85,8 @@ def load_library(path: str | None = None):
     L.anyseq_last_error.argtypes = []
     L.anyseq_ctx_tune.restype = C.c_int
     L.anyseq_ctx_tune.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.anyseq_ctx_set_option.restype = C.c_int
+    L.anyseq_ctx_set_option.argtypes = [vp, cp, C.c_int]
     L.anyseq_score.restype = C.c_int
     L.anyseq_score.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.POINTER(Result)]
     L.anyseq_score_device.restype = C.c_int

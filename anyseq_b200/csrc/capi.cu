@@ -60,6 +60,24 @@ int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int block
     return ANYSEQ_OK;
 }
 
+int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return ANYSEQ_ERR_BAD_ARG;
+    const std::string n(name);
+    anyseq::Tuning& t = ctx->eng.tune;
+    if (n == "cols_per_lane") t.cols_per_lane = value;
+    else if (n == "band_rows") t.band_rows = value;
+    else if (n == "blocks_per_sm") t.blocks_per_sm = value;
+    else if (n == "watchdog_ms") t.watchdog_ms = value;
+    else if (n == "force_generic") t.force_generic = value != 0;
+    else if (n == "align_with_score") t.align_with_score = value != 0;
+    else {
+        set_last_error("unknown option " + n);
+        return ANYSEQ_ERR_BAD_ARG;
+    }
+    return ANYSEQ_OK;
+}
+
 int anyseq_score(anyseq_ctx* ctx, const anyseq_scoring* sc, const char* query, int lenq,
                  const char* subject, int lens, anyseq_result* out)
 {

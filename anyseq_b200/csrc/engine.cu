@@ -113,27 +113,63 @@ __global__ void finish_score_kernel(const Job* __restrict__ jobs, int mode, int 
 }
 
 // ---------------------------------------------------------------------------
-// kernel dispatch
+// kernel dispatch (instantiations live in strip_inst_*.cu)
 // ---------------------------------------------------------------------------
-using KernelFn = void (*)(const KernelArgs);
+using KernelFn = StripKernelFn;
 
-static KernelFn pick_kernel(bool local, bool affine, int K)
+static KernelFn pick_kernel(bool local, bool affine, int K, bool mask)
 {
-#define ANYSEQ_PICK(L, A)                                             \
-    switch (K) {                                                      \
-        case 4: return strip_kernel<L, A, 4>;                         \
-        case 8: return strip_kernel<L, A, 8>;                         \
-        case 16: return strip_kernel<L, A, 16>;                       \
-        case 32: return strip_kernel<L, A, 32>;                       \
-        default: return nullptr;                                      \
+    if (local) return affine ? get_strip_kernel_11(K, mask) : get_strip_kernel_10(K, mask);
+    return affine ? get_strip_kernel_01(K, mask) : get_strip_kernel_00(K, mask);
+}
+
+static size_t mask_smem_bytes(bool mask, int ncodes)
+{
+    return mask ? sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock : 0;
+}
+
+// ---------------------------------------------------------------------------
+// alphabet analysis for the MASK kernels.  Symbols are compared as raw bytes
+// (src/align.impala:132), so any equality-preserving recoding is legal: bytes
+// that occur in BOTH sequences get codes 1..A, every other byte gets code 0,
+// which matches nothing (its column mask is empty).
+// ---------------------------------------------------------------------------
+__global__ void alphabet_presence_kernel(const uint8_t* __restrict__ p, long long n, unsigned* __restrict__ bits /* [8] */)
+{
+    __shared__ unsigned s_bits[8];
+    if (threadIdx.x < 8) s_bits[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned b = p[i];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) loc[w] |= ((b >> 5) == (unsigned)w) ? (1u << (b & 31)) : 0u;
     }
-    if (local) {
-        if (affine) { ANYSEQ_PICK(true, true) } else { ANYSEQ_PICK(true, false) }
-    } else {
-        if (affine) { ANYSEQ_PICK(false, true) } else { ANYSEQ_PICK(false, false) }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        unsigned v = loc[w];
+        for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_bits[w], v);
     }
-#undef ANYSEQ_PICK
-    return nullptr;
+    __syncthreads();
+    if (threadIdx.x < 8 && s_bits[threadIdx.x]) atomicOr(&bits[threadIdx.x], s_bits[threadIdx.x]);
+}
+
+// bits_q/bits_s [8] -> lut_q/lut_s [256], *ncodes = 1 + number of shared symbols
+__global__ void build_lut_kernel(const unsigned* __restrict__ bits_q, const unsigned* __restrict__ bits_s,
+                                 uint8_t* __restrict__ lut_q, uint8_t* __restrict__ lut_s, int* __restrict__ ncodes)
+{
+    if (threadIdx.x == 0) {
+        int next = 1;
+        for (int b = 0; b < 256; ++b) {
+            const bool both = ((bits_q[b >> 5] >> (b & 31)) & 1u) && ((bits_s[b >> 5] >> (b & 31)) & 1u);
+            int code = 0;
+            if (both) { code = next < 255 ? next : 255; ++next; }
+            lut_q[b] = (uint8_t)code;
+            lut_s[b] = (uint8_t)code;
+        }
+        *ncodes = next;
+    }
 }
 
 int Engine::init(int dev)
@@ -166,6 +202,7 @@ int Engine::init(int dev)
     if ((env = std::getenv("ANYSEQ_BLOCKS_PER_SM"))) tune.blocks_per_sm = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_WATCHDOG_MS"))) tune.watchdog_ms = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_ALIGN_SCORE"))) tune.align_with_score = std::atoi(env) != 0;
+    if ((env = std::getenv("ANYSEQ_FORCE_GENERIC"))) tune.force_generic = std::atoi(env) != 0;
     return ANYSEQ_OK;
 }
 
@@ -173,7 +210,7 @@ void Engine::destroy()
 {
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &colH_, &colE_, &rowH_, &rowF_, &corner_,
-                            &progress_, &jobs_, &misc_, &colH2_, &colE2_, &aux_, &aux2_, &pred_,
+                            &progress_, &jobs_, &misc_, &lut_, &colH2_, &colE2_, &aux_, &aux2_, &pred_,
                             &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_};
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
@@ -185,12 +222,34 @@ void Engine::destroy()
 
 int Engine::resident_warps(int K, bool local, bool affine)
 {
-    KernelFn fn = pick_kernel(local, affine, K);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_);
     if (!fn) return 0;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, ncodes_)) != cudaSuccess) return 0;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
     return nb * kWarpsPerBlock * sm_count;
+}
+
+// Decide between the MASK and the generic kernels for a (query, subject) pair
+// that is resident in device memory; builds the byte -> code tables.
+int Engine::analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n)
+{
+    if (lut_.ensure(512 + 64 + 16)) return ANYSEQ_ERR_NO_DEVICE;
+    unsigned* bits = reinterpret_cast<unsigned*>(lut_.as<uint8_t>() + 512);   // [16] presence, then ncodes
+    int* d_ncodes = reinterpret_cast<int*>(bits + 16);
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(bits, 0, sizeof(unsigned) * 17, stream_));
+    const int gq = (int)std::min<long long>(sm_count * 8, (m + 255) / 256);
+    const int gs = (int)std::min<long long>(sm_count * 8, (n + 255) / 256);
+    alphabet_presence_kernel<<<std::max(gq, 1), 256, 0, stream_>>>(d_q, m, bits);
+    alphabet_presence_kernel<<<std::max(gs, 1), 256, 0, stream_>>>(d_s, n, bits + 8);
+    build_lut_kernel<<<1, 32, 0, stream_>>>(bits, bits + 8, lut_.as<uint8_t>(), lut_.as<uint8_t>() + 256, d_ncodes);
+    ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_ + kMiscWords - 1, d_ncodes, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    ncodes_ = h_misc_[kMiscWords - 1];
+    use_mask_ = ncodes_ <= kMaxCodes && !tune.force_generic;
+    if (!use_mask_) ncodes_ = 1;
+    return ANYSEQ_OK;
 }
 
 int Engine::pick_K(int n) const
@@ -200,7 +259,7 @@ int Engine::pick_K(int n) const
         return tune.cols_per_lane;
     // widest strips (least per-step overhead) that still give every resident
     // warp its own strip: ~2400 warps at K=32, ~3000 at K=16, ~3600 at K=8
-    if (n >= 2400 * 1024) return 32;
+    if (n >= 2400 * 1024 && use_mask_) return 32;   // generic kernels: byte registers, K <= 16
     if (n >= 3000 * 512) return 16;
     if (n >= 3600 * 256) return 8;
     return 4;
@@ -239,10 +298,11 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
                                       cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
 
-    KernelFn fn = pick_kernel(local, affine, K);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
+    const size_t dyn_smem = mask_smem_bytes(use_mask_, ncodes_);
     int nb = 0;
-    ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, 0));
+    ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
     long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -261,10 +321,18 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ka.total_items = total;
     ka.sp = sp;
     ka.one = 1;
+    ka.ncodes = ncodes_;
+    ka.lut_q = lut_.as<uint8_t>();
+    ka.lut_s = lut_.as<uint8_t>() + 256;
     ka.status = misc_.as<int>() + kMiscStatus;
+    ka.next_item = reinterpret_cast<unsigned long long*>(misc_.as<int>() + kMiscCounter);
+    {
+        const unsigned long long first = (unsigned long long)grid * kWarpsPerBlock;
+        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ka.next_item, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
+    }
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
     void* args[] = {&ka};
-    ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, 0, stream_));
+    ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, dyn_smem, stream_));
     if (launches) *launches += 2;
     return ANYSEQ_OK;
 }
@@ -329,6 +397,9 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int w = col_end - col_begin;
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
     const bool local = sc.mode == ANYSEQ_LOCAL;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    rc = analyse_alphabet(d_q, m, d_s_slice, w);
+    if (rc) return rc;
     const int K = pick_K(w);
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
@@ -365,7 +436,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     std::vector<Job> jobs(1, J);
     int launches = 0;
     init_col0_ = col_begin;
-    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    launches += 3;   // alphabet analysis
     rc = run_jobs(jobs, sp, local, affine, K, &launches);
     init_col0_ = 0;
     if (rc) return rc;

@@ -39,6 +39,7 @@ struct Tuning {
     int band_rows = 0;       // 0 = auto
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
+    bool force_generic = false;     // never use the MASK kernels (testing)
     bool align_with_score = true;   // anyseq_align also computes the optimal score (one more m*n pass)
 };
 
@@ -47,6 +48,7 @@ enum MiscWord : int {
     kMiscStatus = 0,     // 4 words
     kMiscBest = 4,       // local running maximum
     kMiscOut = 8,        // 8 words: finish kernel output
+    kMiscCounter = 16,   // 2 words (8-byte aligned): work-item counter of the strip kernel
     kMiscWords = 32
 };
 
@@ -98,17 +100,21 @@ private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
                  int* launches);
     int pick_K(int n) const;
+    int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int pick_band(int m, int nstrips, int resident) const;
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     DeviceBuffer seq_q_, seq_s_, seq_qr_, seq_sr_;
     DeviceBuffer colH_, colE_, rowH_, rowF_, corner_, progress_, jobs_, misc_;
+    DeviceBuffer lut_;                // byte -> code tables of the MASK kernels + presence bits
     DeviceBuffer colH2_, colE2_;      // second column set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
     int* h_misc_ = nullptr;           // pinned mirror of misc_
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
+    int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)
+    bool use_mask_ = false;
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
     std::recursive_mutex mu_;
 };

@@ -1,0 +1,31 @@
+// strip_inst.inl -- explicit instantiation of the strip kernels of one
+// (LOCAL, AFFINE) pair; included by strip_inst_XY.cu with ANYSEQ_INST_LOCAL,
+// ANYSEQ_INST_AFFINE and ANYSEQ_INST_NAME defined (4 translation units so the
+// 32 kernels compile in parallel).
+#include "strip_kernel.cuh"
+
+namespace anyseq {
+
+StripKernelFn ANYSEQ_INST_NAME(int K, bool mask)
+{
+    constexpr bool L = ANYSEQ_INST_LOCAL;
+    constexpr bool A = ANYSEQ_INST_AFFINE;
+    if (mask) {
+        switch (K) {
+            case 4: return strip_kernel<L, A, 4, true>;
+            case 8: return strip_kernel<L, A, 8, true>;
+            case 16: return strip_kernel<L, A, 16, true>;
+            case 32: return strip_kernel<L, A, 32, true>;
+            default: return nullptr;
+        }
+    }
+    switch (K) {
+        case 4: return strip_kernel<L, A, 4, false>;
+        case 8: return strip_kernel<L, A, 8, false>;
+        case 16: return strip_kernel<L, A, 16, false>;
+        case 32: return strip_kernel<L, A, 32, false>;
+        default: return nullptr;
+    }
+}
+
+}  // namespace anyseq

@@ -1,0 +1,5 @@
+// strip kernels with LOCAL=1, AFFINE=1 (see strip_inst.inl)
+#define ANYSEQ_INST_LOCAL true
+#define ANYSEQ_INST_AFFINE true
+#define ANYSEQ_INST_NAME get_strip_kernel_11
+#include "strip_inst.inl"

@@ -10,13 +10,19 @@
 //     columns of H (and F for Gotoh) in registers for the whole band,
 //   * lane l works on row t-l at step t (anti-diagonal across lanes); the
 //     right edge (H, E) moves to lane l+1 with warp shuffles,
-//   * the cell update is DPX: VIADDMNMX / VIMNMX3(.RELU) (one instruction per
-//     max(a+b,c) / max(a,b,c)),
+//   * the cell update is DPX on the ALU pipe (VIADDMNMX, VIMNMX3[.RELU]) with
+//     every plain add moved to the FMA pipe as IMAD -- the B200 issues both
+//     pipes side by side at 64 lanes/clk/SM each (microbench.cu),
+//   * symbol comparison: MASK kernels keep, per lane, one 32-bit column mask
+//     per alphabet code in shared memory; the row's query code selects a mask
+//     (one LDS, prefetched a row ahead) and the per-cell predicate is a bit
+//     test that ptxas folds into R2P (7 predicates per instruction); generic
+//     kernels (alphabets with > 32 shared symbols) compare byte registers,
 //   * strips are chained through HBM/L2: lane 31's edge is staged in shared
 //     memory and published 32 rows at a time (coalesced, .cg) with a
 //     release/acquire row counter per strip -- no kernel relaunch, no grid
 //     barrier (the reference relaunches per block anti-diagonal),
-//   * a persistent grid takes (band, strip) items in dependency order, so all
+//   * a persistent grid claims (band, strip) items in dependency order, so all
 //     waits are on lower-numbered items: deadlock-free when co-resident.
 //
 // Score domain: signed 32-bit, identical to the reference (Score = i32,
@@ -33,6 +39,7 @@ namespace anyseq {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * kWarp;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxCodes = 32;      // MASK kernels: alphabet codes incl. code 0 = "matches nothing"
 
 struct KernelArgs {
     const Job* jobs;
@@ -40,7 +47,11 @@ struct KernelArgs {
     long long total_items;
     ScoreParams sp;
     int one;                        // == 1, opaque to the compiler (see imad_add)
+    int ncodes;                     // MASK kernels: number of alphabet codes (<= kMaxCodes)
+    const uint8_t* lut_q;           // MASK kernels: byte -> code for query / subject symbols
+    const uint8_t* lut_s;
     int* status;                    // [0] StatusCode, [1..3] diagnostics
+    unsigned long long* next_item;  // work counter, initialised to the number of resident warps
     unsigned long long timeout_ns;  // watchdog for dependency waits
 };
 
@@ -72,9 +83,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 // a + b on the FMA pipe: IMAD with a multiplier the compiler cannot fold (one == 1
-// at run time).  The B200 issues IMAD (FMA pipe) and DPX/compare ops (ALU pipe)
-// side by side at 64 lanes/clk/SM each (measured: microbench.cu kind 4), so every
-// add moved here is an ALU slot freed for VIADDMNMX / VIMNMX3.
+// at run time).  Every add moved here is an ALU slot freed for VIADDMNMX / VIMNMX3.
 __device__ __forceinline__ int imad_add(int a, int one, int b)
 {
     int r;
@@ -89,6 +98,16 @@ __device__ __forceinline__ int diag_plus_sigma(int qc, int sc, int d, int one, i
     asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tmad.lo.s32 %0, %3, %4, %5;\n\t@p mad.lo.s32 %0, %3, %4, %6;\n\t}"
         : "=&r"(dd)
         : "r"(qc), "r"(sc), "r"(d), "r"(one), "r"(diff), "r"(same));
+    return dd;
+}
+// same with the match predicate taken from bit C of the row's column mask
+template <int C>
+__device__ __forceinline__ int diag_plus_sigma_mask(unsigned mask, int d, int one, int diff, int same)
+{
+    int dd;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tmad.lo.s32 %0, %3, %4, %5;\n\t@p mad.lo.s32 %0, %3, %4, %6;\n\t}"
+        : "=&r"(dd)
+        : "r"(mask), "n"(1u << C), "r"(d), "r"(one), "r"(diff), "r"(same));
     return dd;
 }
 
@@ -126,35 +145,95 @@ __device__ __forceinline__ bool wait_rows(const int* flag, int need, bool sys, i
 template <int K>
 __device__ __forceinline__ void load_row_ints(const int* __restrict__ p, int (&dst)[K])
 {
-    if constexpr (K % 4 == 0) {
 #pragma unroll
-        for (int c = 0; c < K; c += 4) {
-            const int4 v = __ldcg(reinterpret_cast<const int4*>(p + c));
-            dst[c] = v.x; dst[c + 1] = v.y; dst[c + 2] = v.z; dst[c + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < K; ++c) dst[c] = __ldcg(p + c);
+    for (int c = 0; c < K; c += 4) {
+        const int4 v = __ldcg(reinterpret_cast<const int4*>(p + c));
+        dst[c] = v.x; dst[c + 1] = v.y; dst[c + 2] = v.z; dst[c + 3] = v.w;
     }
 }
+
+// state of one lane during one anti-diagonal step
+struct StepState {
+    int dd;          // H(i-1, j-1) + sigma of the cell about to be relaxed
+    int e;           // E of the cell to the left
+    int xleft;       // X (= H [+ open]) of the cell to the left
+    int best;        // LOCAL: running maximum
+    int hprev;       // LOCAL: H of the previous (even) column, folded pairwise with VIMNMX3
+    int es;          // PARTIAL: E of the edge column
+    unsigned mask;   // MASK: columns whose subject symbol equals the row's query symbol
+    int qc;          // !MASK: the row's query byte
+};
+
+struct StepConst {
+    int one, ge, go, diff_o, same_o;
+    int nvalid, outc;   // PARTIAL only
+};
+
+// Cell C of the lane's K columns, then cell C+1, ... (compile-time recursion so
+// that the mask bit is an immediate).  Per cell (SASS, cuobjdump):
+//   Gotoh : VIADDMNMX (E), VIADDMNMX (F), VIMNMX3[.RELU] + 1/7 R2P | IMAD, @p IMAD, IMAD
+//   linear: VIMNMX, VIADDMNMX[.RELU]               + 1/7 R2P | IMAD, @p IMAD
+// The diagonal term of cell C+1 is formed before X[C] is overwritten, so the
+// old value dies in place and no register moves are needed.
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int C>
+struct Cell {
+    template <int KF, int KS>
+    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState& s,
+                                               const StepConst& k)
+    {
+        const int up = X[C];
+        const int dd = s.dd;
+        if constexpr (C + 1 < K) {
+            if constexpr (MASK) s.dd = diag_plus_sigma_mask<C + 1>(s.mask, up, k.one, k.diff_o, k.same_o);
+            else s.dd = diag_plus_sigma(s.qc, sc[C + 1], up, k.one, k.diff_o, k.same_o);
+        }
+        int h;
+        if constexpr (AFFINE) {
+            s.e = __viaddmax_s32(s.e, k.ge, s.xleft);
+            if constexpr (PARTIAL) {
+                if (C == k.outc) s.es = s.e;
+            }
+            const int f = __viaddmax_s32(F[C], k.ge, up);
+            h = LOCAL ? __vimax3_s32_relu(dd, s.e, f) : __vimax3_s32(dd, s.e, f);
+            F[C] = f;
+        } else {
+            const int tmax = max(s.xleft, up);
+            h = LOCAL ? __viaddmax_s32_relu(tmax, k.ge, dd) : __viaddmax_s32(tmax, k.ge, dd);
+        }
+        if constexpr (LOCAL) {
+            if constexpr (PARTIAL) {
+                if (C < k.nvalid) s.best = max(s.best, h);
+            } else if constexpr ((C & 1) != 0) {
+                s.best = __vimax3_s32(s.best, s.hprev, h);
+            } else {
+                s.hprev = h;
+            }
+        }
+        const int x = AFFINE ? imad_add(h, k.one, k.go) : h;
+        X[C] = x;
+        s.xleft = x;
+        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, C + 1>::run(X, F, sc, s, k);
+    }
+};
+
+// shared memory of one warp
+struct WarpSmem {
+    int2 in[32];        // left border rows of the current 32-row batch (X form, E)
+    int2 out[64];       // right edge rows waiting to be published (ring)
+    uint8_t q[64];      // query symbols (MASK: codes) of the last 64 rows (ring)
+};
 
 // One (band, strip) item.  PARTIAL = the strip is cut by the right matrix edge
 // (only the last strip of a job can be): the columns past the edge compute
 // don't-care values (dependencies only run left->right, so they never reach a
 // valid cell), the edge column is picked out for the output, and the local
 // maximum is masked.
-//
-// Instruction budget per cell (SASS, checked with cuobjdump):
-//   Gotoh : ISETP, VIADDMNMX (E), VIADDMNMX (F), VIMNMX3[.RELU]   -> 4 ALU
-//           IMAD, @p IMAD (diag + sigma), IMAD (X = H + open)     -> 3 FMA
-//   linear: ISETP, VIMNMX, VIADDMNMX[.RELU]                       -> 3 ALU
-//           IMAD, @p IMAD                                         -> 2 FMA
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL>
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
-                                             const ScoreParams& sp, const int one,
-                                             int2* __restrict__ s_in, int2* __restrict__ s_out,
-                                             uint8_t* __restrict__ s_q, const int lane, int* status,
-                                             const unsigned long long timeout_ns)
+                                             const KernelArgs& a, WarpSmem& sm,
+                                             unsigned* __restrict__ s_mask /* [ncodes][32] */,
+                                             const uint8_t* __restrict__ s_lut /* [2][256] */,
+                                             const int lane)
 {
     constexpr int SW = kWarp * K;
     const int i0 = band * J.band_h;
@@ -162,9 +241,15 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     const int j0 = strip * SW;
     const int wv = min(SW, J.w - j0);
     const bool last_strip = (strip == J.nstrips - 1);
-    const int go = AFFINE ? sp.gap_open : 0;
-    const int ge = sp.gap_extend;
-    const int same_o = sp.same - go, diff_o = sp.diff - go;
+    const int go = AFFINE ? a.sp.gap_open : 0;
+    StepConst k;
+    k.one = a.one;
+    k.ge = a.sp.gap_extend;
+    k.go = go;
+    k.diff_o = a.sp.diff - go;
+    k.same_o = a.sp.same - go;
+    int* const status = a.status;
+    const unsigned long long timeout_ns = a.timeout_ns;
 
     // left border source (rows of this band)
     const int* linH;
@@ -189,18 +274,34 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         if (!wait_rows(J.progress + strip, i0, false, status, timeout_ns)) return false;
     }
 
-    int X[K], F[K], sc[K];
+    int X[K], F[AFFINE ? K : 1], sc[MASK ? 1 : K];
     const int jl = j0 + lane * K;
     load_row_ints<K>(J.rowH + jl, X);
     if constexpr (AFFINE) {
         load_row_ints<K>(J.rowF + jl, F);
 #pragma unroll
         for (int c = 0; c < K; ++c) X[c] += go;
+    } else {
+        F[0] = 0;
     }
+    if constexpr (MASK) {
+        // per-lane column masks, one per alphabet code; code 0 matches nothing
+        sc[0] = 0;
+        __syncwarp();
+        for (int cd = 0; cd < a.ncodes; ++cd) s_mask[cd * 32 + lane] = 0u;
+#pragma unroll 4
+        for (int c = 0; c < K; ++c) {
+            const int j = jl + c;
+            const int cd = (j < J.w) ? (int)s_lut[256 + J.s[j]] : 0;
+            if (cd) s_mask[cd * 32 + lane] |= 1u << c;
+        }
+        __syncwarp();
+    } else {
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-        const int j = jl + c;
-        sc[c] = (j < J.w) ? (int)J.s[j] : 0x7fff;   // never equals a byte
+        for (int c = 0; c < K; ++c) {
+            const int j = jl + c;
+            sc[c] = (j < J.w) ? (int)J.s[j] : 0x7fff;   // never equals a byte
+        }
     }
 
     // H(i0-1, first column - 1) in X form
@@ -208,18 +309,26 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     if (lane == 0) dcarry = __ldcg(J.corner + strip) + go;
 
     const int outlane = PARTIAL ? (wv - 1) / K : 31;
-    const int outc = PARTIAL ? (wv - 1) % K : K - 1;
-    const int nvalid = PARTIAL ? max(0, min(K, wv - lane * K)) : K;
+    k.outc = PARTIAL ? (wv - 1) % K : K - 1;
+    k.nvalid = PARTIAL ? max(0, min(K, wv - lane * K)) : K;
     const int T = hb + outlane;            // number of steps
     int hr = 0, er = 0;
-    int best = kScoreMin;
     int flushed = 0;
+    StepState st;
+    st.dd = 0;
+    st.e = 0;
+    st.xleft = 0;
+    st.best = kScoreMin;
+    st.hprev = kScoreMin;
+    st.es = 0;
+    st.mask = 0u;
+    st.qc = 0;
 
     auto flush32 = [&](int base) {
         // rows [base, base+32) of the out lane's edge -> colH/colE (coalesced)
         const int r = base + lane;
         if (r < hb) {
-            const int2 v = s_out[r & 63];
+            const int2 v = sm.out[r & 63];
             __stcg(J.colH + i0 + r, v.x - go);
             if constexpr (AFFINE) __stcg(J.colE + i0 + r, v.y);
             if (mirror) {
@@ -239,6 +348,8 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             st_relaxed_gpu(J.progress + strip, rows_abs);
         }
     };
+    // MASK: column mask of row i (its query code selects one of the lane's masks)
+    auto row_mask = [&](int i) -> unsigned { return s_mask[(int)sm.q[i & 63] * 32 + lane]; };
 
     // one anti-diagonal step; GUARD = some lanes may be outside [0, hb)
     auto step = [&](auto guard_tag, const int t) {
@@ -246,56 +357,39 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         int xl = __shfl_up_sync(kFull, hr, 1);
         int el = 0;
         if constexpr (AFFINE) el = __shfl_up_sync(kFull, er, 1);
-        const int2 bnd = s_in[t & 31];
+        const int2 bnd = sm.in[t & 31];
         if (lane == 0) { xl = bnd.x; el = bnd.y; }
         const int i = t - lane;
+        unsigned mask_next = 0u;
+        if constexpr (MASK) mask_next = row_mask(i + 1);      // prefetch, off the critical path
         if (!GUARD || (unsigned)i < (unsigned)hb) {
-            const int qc = s_q[i & 63];
-            int d = dcarry;
-            dcarry = xl;
-            int xleft = xl;
-            int e = el;
-            int es = 0;   // PARTIAL: E of the edge column
-#pragma unroll
-            for (int c = 0; c < K; ++c) {
-                const int up = X[c];
-                int h;
-                if constexpr (AFFINE) {
-                    const int dd = diag_plus_sigma(qc, sc[c], d, one, diff_o, same_o);
-                    e = __viaddmax_s32(e, ge, xleft);
-                    if constexpr (PARTIAL) {
-                        if (c == outc) es = e;
-                    }
-                    const int f = __viaddmax_s32(F[c], ge, up);
-                    h = LOCAL ? __vimax3_s32_relu(dd, e, f) : __vimax3_s32(dd, e, f);
-                    F[c] = f;
-                } else {
-                    const int dd = diag_plus_sigma(qc, sc[c], d, one, sp.diff, sp.same);
-                    const int tmax = max(xleft, up);
-                    h = LOCAL ? __viaddmax_s32_relu(tmax, ge, dd) : __viaddmax_s32(tmax, ge, dd);
-                }
-                if constexpr (LOCAL) {
-                    if (!PARTIAL || c < nvalid) best = max(best, h);
-                }
-                const int x = AFFINE ? imad_add(h, one, go) : h;
-                d = up;
-                X[c] = x;
-                xleft = x;
+            if constexpr (MASK) {
+                st.dd = diag_plus_sigma_mask<0>(st.mask, dcarry, k.one, k.diff_o, k.same_o);
+            } else {
+                st.qc = sm.q[i & 63];
+                st.dd = diag_plus_sigma(st.qc, sc[0], dcarry, k.one, k.diff_o, k.same_o);
             }
-            hr = xleft;
-            er = e;
+            dcarry = xl;
+            st.xleft = xl;
+            st.e = el;
+            Cell<LOCAL, AFFINE, K, PARTIAL, MASK, 0>::run(X, F, sc, st, k);
+            hr = st.xleft;
+            er = st.e;
             if constexpr (PARTIAL) {
                 if (lane == outlane) {
                     int hs = X[0];
 #pragma unroll
                     for (int c = 1; c < K; ++c)
-                        if (c == outc) hs = X[c];
-                    s_out[i & 63] = make_int2(hs, es);
+                        if (c == k.outc) hs = X[c];
+                    sm.out[i & 63] = make_int2(hs, st.es);
                 }
             } else {
-                if (lane == 31) s_out[i & 63] = make_int2(hr, er);
+                if (lane == 31) sm.out[i & 63] = make_int2(hr, er);
             }
         }
+        // also on steps where this lane is still above the band: its first row
+        // must find the mask of row 0 in place
+        if constexpr (MASK) st.mask = mask_next;
     };
 
     for (int tb = 0; tb < T; tb += 32) {
@@ -323,12 +417,13 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 if (r < hb) {
                     v.x = __ldcg(linH + r) + go;
                     if constexpr (AFFINE) v.y = __ldcg(linE + r);
-                    qv = qrow[r];
+                    qv = MASK ? s_lut[qrow[r]] : qrow[r];
                 }
             }
-            s_in[lane] = v;
-            s_q[r & 63] = qv;
+            sm.in[lane] = v;
+            sm.q[r & 63] = qv;
             __syncwarp();
+            if constexpr (MASK) st.mask = row_mask(tb - lane);   // row of this lane at step tb
         }
         // (3) 32 anti-diagonal steps; batches in which every lane is inside the
         //     band run the unguarded body
@@ -348,26 +443,16 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         flush32(flushed);
         flushed += 32;
     }
-    {
-        if constexpr (K % 4 == 0) {
 #pragma unroll
-            for (int c = 0; c < K; c += 4) {
-                __stcg(reinterpret_cast<int4*>(J.rowH + jl + c),
-                       make_int4(X[c] - go, X[c + 1] - go, X[c + 2] - go, X[c + 3] - go));
-                if constexpr (AFFINE)
-                    __stcg(reinterpret_cast<int4*>(J.rowF + jl + c),
-                           make_int4(F[c], F[c + 1], F[c + 2], F[c + 3]));
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < K; ++c) {
-                __stcg(J.rowH + jl + c, X[c] - go);
-                if constexpr (AFFINE) __stcg(J.rowF + jl + c, F[c]);
-            }
-        }
-        if (lane == 0) __stcg(J.corner + strip, dcarry - go);
+    for (int c = 0; c < K; c += 4) {
+        __stcg(reinterpret_cast<int4*>(J.rowH + jl + c),
+               make_int4(X[c] - go, X[c + 1] - go, X[c + 2] - go, X[c + 3] - go));
+        if constexpr (AFFINE)
+            __stcg(reinterpret_cast<int4*>(J.rowF + jl + c), make_int4(F[c], F[c + 1], F[c + 2], F[c + 3]));
     }
+    if (lane == 0) __stcg(J.corner + strip, dcarry - go);
     if constexpr (LOCAL) {
+        int best = st.best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
         if (lane == 0) atomicMax(J.best, best);
@@ -376,25 +461,47 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     return true;
 }
 
-// registers per thread are capped so that 4 CTAs (16 warps, 4 per scheduler)
-// fit on an SM for every K: the recurrence has a 3-deep dependent chain per cell
-// and needs that many warps to keep the ALU pipe busy.
-template <bool LOCAL, bool AFFINE, int K>
-__global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6)))
-strip_kernel(const KernelArgs a)
+// CTAs per SM the register allocation is capped for: the recurrence has a 3-deep
+// dependent chain per cell and needs >= 4 warps per scheduler to hide it.
+template <int K, bool MASK>
+constexpr int strip_min_blocks()
 {
-    __shared__ int2 s_in[kWarpsPerBlock][32];
-    __shared__ int2 s_out[kWarpsPerBlock][64];
-    __shared__ uint8_t s_q[kWarpsPerBlock][64];
+#ifndef ANYSEQ_K32_MASK_BLOCKS
+#define ANYSEQ_K32_MASK_BLOCKS 4
+#endif
+    return K >= 32 ? (MASK ? ANYSEQ_K32_MASK_BLOCKS : 4) : (K >= 16 ? 5 : 6);
+}
+
+template <bool LOCAL, bool AFFINE, int K, bool MASK>
+__global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_kernel(const KernelArgs a)
+{
+    __shared__ WarpSmem s_warp[kWarpsPerBlock];
+    __shared__ uint8_t s_lut[MASK ? 512 : 4];
+    extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32] column masks
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     constexpr int SW = kWarp * K;
+    if constexpr (MASK) {
+        for (int x = threadIdx.x; x < 256; x += kThreads) {
+            s_lut[x] = a.lut_q[x];
+            s_lut[256 + x] = a.lut_s[x];
+        }
+        __syncthreads();
+    }
+    unsigned* s_mask = s_dyn + warp * a.ncodes * 32;
+    // the query ring is read one row ahead (mask prefetch): never let an
+    // uninitialised byte be used as a code
+    s_warp[warp].q[lane] = 0;
+    s_warp[warp].q[32 + lane] = 0;
+    __syncwarp();
 
+    // Items are claimed in index order from a global counter (the first round is
+    // the static assignment): every item only waits on lower-numbered items, which
+    // were claimed earlier by warps that are resident, so no wait can be circular.
     int jcur = 0;
-    for (long long item = (long long)blockIdx.x * kWarpsPerBlock + warp; item < a.total_items;
-         item += nwarps) {
+    long long item = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    for (; item < a.total_items;) {
         while (jcur + 1 < a.njobs && item >= a.jobs[jcur + 1].item_begin) ++jcur;
         const Job& J = a.jobs[jcur];
         const long long loc = item - J.item_begin;
@@ -403,15 +510,21 @@ strip_kernel(const KernelArgs a)
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)
-            ok = process_item<LOCAL, AFFINE, K, true>(J, band, strip, a.sp, a.one, s_in[warp],
-                                                      s_out[warp], s_q[warp], lane, a.status,
-                                                      a.timeout_ns);
+            ok = process_item<LOCAL, AFFINE, K, true, MASK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         else
-            ok = process_item<LOCAL, AFFINE, K, false>(J, band, strip, a.sp, a.one, s_in[warp],
-                                                       s_out[warp], s_q[warp], lane, a.status,
-                                                       a.timeout_ns);
+            ok = process_item<LOCAL, AFFINE, K, false, MASK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         if (!ok) return;
+        unsigned long long nxt = 0;
+        if (lane == 0) nxt = atomicAdd(a.next_item, 1ull);
+        item = (long long)__shfl_sync(kFull, nxt, 0);
     }
 }
+
+using StripKernelFn = void (*)(const KernelArgs);
+// defined in strip_inst_*.cu (one translation unit per (LOCAL, AFFINE) pair)
+StripKernelFn get_strip_kernel_00(int K, bool mask);
+StripKernelFn get_strip_kernel_01(int K, bool mask);
+StripKernelFn get_strip_kernel_10(int K, bool mask);
+StripKernelFn get_strip_kernel_11(int K, bool mask);
 
 }  // namespace anyseq

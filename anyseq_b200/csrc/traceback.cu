@@ -278,6 +278,9 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
     int* d_splits = aux_.as<int>();
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(d_splits, splits.data(), sizeof(int) * splits.size(), cudaMemcpyHostToDevice, stream_));
 
+    rc = analyse_alphabet(d_q, m, d_s, n);
+    if (rc) return rc;
+    launches += 3;
     const int Ktop = pick_K(n);
     std::vector<Job> jobs;
     std::vector<HbPart> parts;

@@ -104,6 +104,11 @@ const char* anyseq_last_error(void);
  * in rows, persistent blocks per SM, dependency-wait watchdog in ms. */
 int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int blocks_per_sm, int watchdog_ms);
 
+/* Named options: "cols_per_lane", "band_rows", "blocks_per_sm", "watchdog_ms",
+ * "force_generic" (1: byte-register kernels even for small alphabets),
+ * "align_with_score" (0: anyseq_align skips the extra score pass). */
+int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value);
+
 /* Score only: score() of src/align.impala:218-235 with host buffers (the call
  * copies them to the device) ... */
 int anyseq_score(anyseq_ctx* ctx, const anyseq_scoring* sc,

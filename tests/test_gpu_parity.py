@@ -62,12 +62,15 @@ def test_legacy_symbols_appendix_c(oracle, golden):
         assert (aq, as_) == (o[1], o[2])
 
 
-@pytest.mark.parametrize("K,band", [(4, 0), (8, 64), (16, 32), (32, 0), (4, 96), (32, 160)])
-def test_score_sweep_vs_oracle(aligner, oracle, K, band):
-    """all schemes x linear/affine x ragged shapes, every columns-per-lane variant, multi-band"""
+@pytest.mark.parametrize("K,band,generic", [(4, 0, 0), (8, 64, 0), (16, 32, 0), (32, 0, 0), (4, 96, 1), (32, 160, 0),
+                                            (16, 0, 1), (8, 160, 1), (32, 64, 1)])
+def test_score_sweep_vs_oracle(aligner, oracle, K, band, generic):
+    """all schemes x linear/affine x ragged shapes, every columns-per-lane variant, multi-band;
+    generic = byte-register kernels instead of the column-mask kernels"""
     import anyseq_b200 as A
     rng = np.random.default_rng(100 + K + band)
     aligner.tune(cols_per_lane=K, band_rows=band, watchdog_ms=10000)
+    aligner.set_option("force_generic", generic)
     schemes = [A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1),
                A.linear_scoring_scheme(3, -2, -4), A.affine_scoring_scheme(5, -4, -10, -1),
                A.affine_scoring_scheme(1, -1, -1, 0)]
@@ -89,6 +92,7 @@ def test_score_sweep_vs_oracle(aligner, oracle, K, band):
                         assert (r.end_i, r.end_j) == ref[1:], (m, n, mode, sch)
     finally:
         aligner.tune(0, 0, 0, 10000)
+        aligner.set_option("force_generic", 0)
 
 
 def test_score_golden_fixtures(aligner, golden):

@@ -17,10 +17,16 @@ def main():
     Ks = [int(x) for x in (sys.argv[5] if len(sys.argv) > 5 else "16,32").split(",")]
     bands = [int(x) for x in (sys.argv[6] if len(sys.argv) > 6 else "0").split(",")]
     bpss = [int(x) for x in (sys.argv[7] if len(sys.argv) > 7 else "0").split(",")]
-    g = torch.Generator(device="cuda"); g.manual_seed(1)
-    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
-    q = lut[torch.randint(0, 4, (m,), device="cuda", generator=g)]
-    s = lut[torch.randint(0, 4, (n,), device="cuda", generator=g)]
+    reps = int(os.environ.get("REPS", "2"))
+    if os.environ.get("WL"):
+        from anyseq_b200 import workloads as W
+        hq, hs, _ = W.whole_genome_pair(float(os.environ["WL"]))
+        q = torch.from_numpy(hq).cuda(); s = torch.from_numpy(hs).cuda(); m, n = len(hq), len(hs)
+    else:
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
+        q = lut[torch.randint(0, 4, (m,), device="cuda", generator=g)]
+        s = lut[torch.randint(0, 4, (n,), device="cuda", generator=g)]
     torch.cuda.synchronize()
     al = A.Aligner()
     sch = A.affine_scoring_scheme() if affine else A.linear_scoring_scheme()
@@ -29,7 +35,7 @@ def main():
             for bps in bpss:
                 al.tune(cols_per_lane=K, band_rows=band, blocks_per_sm=bps, watchdog_ms=20000)
                 best = 1e30
-                for rep in range(2):
+                for rep in range(reps):
                     r = al.score_device(mode, q.data_ptr(), m, s.data_ptr(), n, sch)
                     best = min(best, r.kernel_ms)
                 print(f"m={m} n={n} affine={affine} {mode} K={K} band={band} bps={bps}: {best:.2f} ms "
