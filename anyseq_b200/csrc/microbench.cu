@@ -9,8 +9,8 @@
 //   kind 2  the 7-op affine-gap cell mix           ISETP SEL IADD 2xVIADDMNMX VIMNMX3 IADD
 //   kind 3  IMAD only                              (FMA pipe)
 //   kind 4  kind 0 and kind 3 interleaved 1:1      (do the pipes dual-issue?)
-//   kind 5  the strip kernel's own Gotoh cell      ISETP 2xVIADDMNMX VIMNMX3 | 3x IMAD
-//   kind 6  the strip kernel's own linear cell     ISETP VIMNMX VIADDMNMX    | 2x IMAD
+//   kind 5  the strip kernel's own Gotoh cell      2xVIADDMNMX VIMNMX3 + R2P/7 | 3x IMAD
+//   kind 6  the strip kernel's own linear cell     VIMNMX VIADDMNMX + R2P/7    | 2x IMAD
 //           (kinds 5/6 return CELLS per second: the cell-update peak of the mix
 //            the kernel really executes, both pipes busy)
 // The result is lane-operations per second over the whole chip.
@@ -20,6 +20,31 @@
 namespace anyseq {
 
 constexpr int kChains = 8;
+
+// kinds 5 / 6: 32 cells of the strip kernel's own instruction sequence (8
+// independent chains x 4), the match predicate taken from bit IDX of a mask
+// exactly as in strip_kernel.cuh (ptxas folds the bit tests into R2P)
+template <int KIND, int IDX>
+struct MixCell {
+    static __device__ __forceinline__ void run(int (&a)[kChains], int (&b)[kChains], int (&c)[kChains],
+                                               int (&d)[kChains], unsigned mask, int p0, int p1, int p2, int p3)
+    {
+        constexpr int k = IDX % kChains;
+        if constexpr (KIND == 5) {
+            const int dd = diag_plus_sigma_mask<IDX>(mask, b[k], p3, p0, p1);
+            const int e = __viaddmax_s32(a[k], p2, b[k]);
+            const int f = __viaddmax_s32(d[k], p2, c[k]);
+            const int h = __vimax3_s32(dd, e, f);
+            a[k] = e; d[k] = f; c[k] = b[k]; b[k] = imad_add(h, p3, p2);
+        } else {
+            const int dd = diag_plus_sigma_mask<IDX>(mask, a[k], p3, p0, p1);
+            const int t = max(b[k], d[k]);
+            const int h = __viaddmax_s32(t, p2, dd);
+            c[k] = a[k]; a[k] = d[k]; d[k] = b[k]; b[k] = h;
+        }
+        if constexpr (IDX + 1 < 4 * kChains) MixCell<KIND, IDX + 1>::run(a, b, c, d, mask, p0, p1, p2, p3);
+    }
+};
 
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(const int* __restrict__ in, int* __restrict__ out,
@@ -38,6 +63,9 @@ __global__ void __launch_bounds__(256) int_peak_kernel(const int* __restrict__ i
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        if constexpr (KIND == 5 || KIND == 6) {
+            MixCell<KIND, 0>::run(a, b, c, d, (unsigned)c[0] ^ (unsigned)it, p0, p1, p2, p3);
+        } else
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -60,17 +88,6 @@ __global__ void __launch_bounds__(256) int_peak_kernel(const int* __restrict__ i
                     const int dd = b[k] + sub;
                     const int h = __vimax3_s32(dd, e, f);
                     a[k] = e; d[k] = f; b[k] = h + p3;
-                } else if constexpr (KIND == 5) {
-                    const int dd = diag_plus_sigma(c[k], p1, b[k], p3, p0, p1);
-                    const int e = __viaddmax_s32(a[k], p2, b[k]);
-                    const int f = __viaddmax_s32(d[k], p2, c[k]);
-                    const int h = __vimax3_s32(dd, e, f);
-                    a[k] = e; d[k] = f; c[k] = b[k]; b[k] = imad_add(h, p3, p2);
-                } else if constexpr (KIND == 6) {
-                    const int dd = diag_plus_sigma(c[k], p1, a[k], p3, p0, p1);
-                    const int t = max(b[k], d[k]);
-                    const int h = __viaddmax_s32(t, p2, dd);
-                    c[k] = a[k]; a[k] = d[k]; d[k] = b[k]; b[k] = h;
                 } else if constexpr (KIND == 3) {
                     a[k] = a[k] * p0 + b[k];
                     b[k] = b[k] * p1 + a[k];

@@ -111,22 +111,38 @@ __device__ __forceinline__ int diag_plus_sigma_mask(unsigned mask, int d, int on
     return dd;
 }
 
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Wait until *flag >= need.  Executed by all lanes of a warp (same address:
-// one transaction).  Returns false if the watchdog fired or another warp
-// already reported a failure -- the caller then leaves the kernel, so a logic
-// error shows up as a status code instead of a hung GPU.
+// one transaction).  The poll is a relaxed load (an acquire load costs a
+// CCTL.IVALL -- a whole-L1 invalidate -- per poll); one acquire fence after the
+// condition holds orders the following border loads.  Returns false if the
+// watchdog fired or another warp already reported a failure -- the caller then
+// leaves the kernel, so a logic error shows up as a status code instead of a
+// hung GPU.
 __device__ __forceinline__ bool wait_rows(const int* flag, int need, bool sys, int* status,
                                           unsigned long long timeout_ns)
 {
     bool ok = true;
-    int v = sys ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
+    int v = sys ? ld_relaxed_sys(flag) : ld_relaxed_gpu(flag);
     if (v < need) {
         const unsigned long long t0 = global_timer_ns();
         unsigned spins = 0;
         while (true) {
-            v = sys ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
+            v = sys ? ld_relaxed_sys(flag) : ld_relaxed_gpu(flag);
             if (v >= need) break;
-            __nanosleep(100);
+            __nanosleep(200);
             if ((++spins & 127u) == 0u) {
                 if (*(volatile int*)status != kStatusOk) { ok = false; break; }
                 if (global_timer_ns() - t0 > timeout_ns) {
@@ -139,6 +155,7 @@ __device__ __forceinline__ bool wait_rows(const int* flag, int need, bool sys, i
             }
         }
     }
+    if (sys) __threadfence_system(); else __threadfence();
     return __all_sync(kFull, ok);
 }
 
