@@ -257,12 +257,22 @@ int Engine::pick_K(int n) const
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
-    // widest strips (least per-step overhead) that still give every resident
-    // warp its own strip: ~2400 warps at K=32, ~3000 at K=16, ~3600 at K=8
-    if (n >= 2400 * 1024 && use_mask_) return 32;   // generic kernels: byte registers, K <= 16
-    if (n >= 3000 * 512) return 16;
-    if (n >= 3600 * 256) return 8;
-    return 4;
+    // Throughput model (cells per clock per GPU).  At most one warp works on a
+    // strip at a time, so min(nstrips, resident warps) warps are busy; a lone warp
+    // is bound by the 3-deep dependent chain per cell (~2.4 cells/clk), a full SM
+    // by issue slots: ~6 per cell plus ~48 per step of K cells of fixed overhead.
+    const double cap = 21.3 * sm_count;
+    double best = -1.0;
+    int bestK = 4;
+    for (int K : {4, 8, 16, 32}) {
+        if (K == 32 && !use_mask_) continue;          // generic kernels keep subject bytes in registers
+        const double eff = 6.0 * K / (6.0 * K + 48.0);
+        const double resident = sm_count * 4.0 * (K >= 32 ? 4 : (K >= 16 ? 5 : 6));
+        const double nstrips = (n + 32.0 * K - 1) / (32.0 * K);
+        const double rate = std::min(cap * eff, std::min(nstrips, resident) * 2.4);
+        if (rate > best * 1.02) { best = rate; bestK = K; }
+    }
+    return bestK;
 }
 
 // Band height.  Items are taken in index order by a window of `resident` warps,

@@ -114,7 +114,7 @@ def run_reference(args, rank):
     from anyseq_b200 import workloads as W
     q, s, desc = W.whole_genome_pair(args.scale)
     threads = os.cpu_count() or 1
-    side = int(args.cpu_sample)
+    side = int(args.cpu_sample) or 150000
     times = []
     for i in range(args.warmup + args.steps):
         g, dt, _ = cpu_baseline(q, s, side, side, threads)
@@ -143,7 +143,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
-    ap.add_argument("--cpu-sample", type=int, default=40000, help="side of the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="side of the CPU-baseline sample (default: 250000 for the cpu_baseline leg, "
+                         "150000 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -282,7 +284,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        side = int(args.cpu_sample)
+        side = int(args.cpu_sample) or 250000
         g, dt, _ = cpu_baseline(q, s, side, side, threads)
         cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
                "sample": f"first {side} x {side} cells of the workload ({dt:.1f} s), restated reference CPU path "

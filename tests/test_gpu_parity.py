@@ -290,3 +290,62 @@ def test_cli_report_format():
         assert ln.startswith("testing " + nm + " ") and ln.endswith(" ms")
     r = subprocess.run([build.CLI, "-r", "10000"], capture_output=True, text=True, timeout=300)
     assert "sequence lengths: 8087, 9011" in r.stdout       # quirk Q7
+
+
+# --------------------------------------------------------------------------- batches
+def _pack(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    data = np.concatenate([np.asarray(x, dtype=np.uint8) for x in seqs]) if off[-1] else np.zeros(0, np.uint8)
+    return data, off
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "bytes"])
+def test_batch_vs_oracle(aligner, oracle, alphabet):
+    """ragged batch (empty, 1-symbol, up to 1024 symbols), every scheme, linear + Gotoh, vs the oracle per pair"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(99)
+    alpha = ACGT if alphabet == "dna" else np.arange(256, dtype=np.uint8)
+    lim = 1024 if alphabet == "dna" else 512
+    qs, ss = [], []
+    for p in range(160):
+        lq = int(rng.integers(0, 200)) if p % 7 else int(rng.integers(0, 3))
+        ls = int(rng.integers(1, lim + 1)) if p % 5 else int(rng.integers(0, 40))
+        q = _rand(rng, lq, alpha)
+        s = _rand(rng, ls, alpha)
+        if lq and ls > lq and p % 3 == 0:          # implant a mutated copy of the read
+            o = int(rng.integers(0, ls - lq + 1)); s[o:o + lq] = q; s[o + lq // 2] = alpha[0]
+        if p % 11 == 0:
+            q, s = s, q                            # long query, short subject
+        qs.append(q); ss.append(s)
+    qd, qo = _pack(qs); sd, so = _pack(ss)
+    for sch in (A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1), A.affine_scoring_scheme(5, -4, -10, -1)):
+        for mode in MODES:
+            got, info = aligner.score_batch(mode, qd, qo, sd, so, sch)
+            for p, (q, s) in enumerate(zip(qs, ss)):
+                if len(q) == 0 or len(s) == 0:
+                    ref = aligner.score(mode, q, s, sch).score       # quirk Q12 values, same as the single-pair path
+                elif sch.affine:
+                    ref = oracle.textbook_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                else:
+                    ref = oracle.textbook_linear(mode, q, s, sch.same, sch.diff, sch.gap_extend)
+                assert got[p] == ref, (alphabet, mode, sch, p, len(q), len(s))
+
+
+def test_batch_reads_vs_windows(aligner, oracle):
+    """BASELINE.json configs[3] shape (150 bp reads vs 500 bp windows), 20k pairs: sample vs oracle, all vs the
+    single-pair strip engine through a 64-bit checksum"""
+    import anyseq_b200 as A
+    from anyseq_b200 import workloads as W
+    npairs = 20000
+    qd, qo, sd, so = W.read_batch(npairs)
+    sch = A.affine_scoring_scheme(2, -1, -2, -1)
+    for mode in ("global", "semiglobal"):
+        got, info = aligner.score_batch(mode, qd, qo, sd, so, sch)
+        for p in range(0, npairs, 97):
+            q, s = qd[qo[p]:qo[p + 1]], sd[so[p]:so[p + 1]]
+            assert got[p] == oracle.textbook_affine(mode, q, s, 2, -1, -2, -1), (mode, p)
+        for p in range(0, 64):
+            q, s = qd[qo[p]:qo[p + 1]], sd[so[p]:so[p + 1]]
+            assert got[p] == aligner.score(mode, q, s, sch).score
+        assert info.kernel_ms > 0

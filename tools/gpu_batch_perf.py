@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""throughput of the batch kernel on the C4 workload shape (reads 150 vs windows 500)"""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import anyseq_b200 as A
+from anyseq_b200 import workloads as W
+npairs = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+qd, qo, sd, so = W.read_batch(npairs)
+dq, dqo, ds, dso = (torch.from_numpy(x).cuda() for x in (qd, qo, sd, so))
+out = torch.zeros(npairs, dtype=torch.int32, device="cuda")
+al = A.Aligner()
+cells = 150.0 * 500.0 * npairs
+for mode in ("global", "semiglobal", "local"):
+    for sch in (A.affine_scoring_scheme(), A.linear_scoring_scheme()):
+        best = 1e30
+        for rep in range(3):
+            r = al.score_batch_device(mode, dq.data_ptr(), dqo.data_ptr(), ds.data_ptr(), dso.data_ptr(), npairs, out.data_ptr(), sch)
+            best = min(best, r.kernel_ms)
+        print(f"batch {npairs} pairs {mode} affine={sch.affine}: {best:.2f} ms {cells/best/1e6:.1f} GCUPS checksum={int(out.to(torch.int64).sum())}", flush=True)
