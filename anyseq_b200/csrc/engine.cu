@@ -123,6 +123,23 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask)
     return affine ? get_strip_kernel_01(K, mask) : get_strip_kernel_00(K, mask);
 }
 
+// rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)
+static int rows_per_step(int K, bool mask)
+{
+    return (mask && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
+}
+
+// CTAs per SM actually launched.  Two-row tiles carry two dependent chains per
+// warp, so two warps per scheduler already saturate the issue slots, and fewer
+// warps per scheduler means less spread in per-warp progress -- which is what
+// the strip-to-strip pipeline is sensitive to (measured: profiles/).
+static int default_blocks_per_sm(int K, bool mask, int occupancy_max)
+{
+    int nb = occupancy_max;
+    if (rows_per_step(K, mask) == 2) nb = std::min(nb, K >= 32 ? 2 : 3);
+    return nb;
+}
+
 static size_t mask_smem_bytes(bool mask, int ncodes)
 {
     return mask ? sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock : 0;
@@ -227,6 +244,7 @@ int Engine::resident_warps(int K, bool local, bool affine)
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, ncodes_)) != cudaSuccess) return 0;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
+    else nb = default_blocks_per_sm(K, use_mask_, nb);
     return nb * kWarpsPerBlock * sm_count;
 }
 
@@ -257,20 +275,23 @@ int Engine::pick_K(int n) const
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
-    // Throughput model (cells per clock per GPU).  At most one warp works on a
-    // strip at a time, so min(nstrips, resident warps) warps are busy; a lone warp
-    // is bound by the 3-deep dependent chain per cell (~2.4 cells/clk), a full SM
-    // by issue slots: ~6 per cell plus ~48 per step of K cells of fixed overhead.
-    const double cap = 21.3 * sm_count;
+    // Throughput model in cells per clock per GPU, constants measured on B200
+    // (profiles/): at most one warp works on a strip at a time, so
+    // min(nstrips, resident warps) warps are busy, each at its lone-warp rate,
+    // up to the rate the whole chip sustains with that kernel variant.
+    struct Variant { int K; double lone; double chip; int blocks; };
+    static const Variant mask_variants[] = {{32, 2.8, 1750.0, 2}, {16, 2.4, 1500.0, 3}, {8, 1.3, 1000.0, 6}, {4, 1.0, 600.0, 6}};
+    static const Variant byte_variants[] = {{16, 1.4, 1300.0, 5}, {8, 1.2, 900.0, 6}, {4, 0.9, 550.0, 6}};
+    const Variant* v = use_mask_ ? mask_variants : byte_variants;
+    const int nv = use_mask_ ? 4 : 3;
     double best = -1.0;
     int bestK = 4;
-    for (int K : {4, 8, 16, 32}) {
-        if (K == 32 && !use_mask_) continue;          // generic kernels keep subject bytes in registers
-        const double eff = 6.0 * K / (6.0 * K + 48.0);
-        const double resident = sm_count * 4.0 * (K >= 32 ? 4 : (K >= 16 ? 5 : 6));
-        const double nstrips = (n + 32.0 * K - 1) / (32.0 * K);
-        const double rate = std::min(cap * eff, std::min(nstrips, resident) * 2.4);
-        if (rate > best * 1.02) { best = rate; bestK = K; }
+    for (int i = 0; i < nv; ++i) {
+        const double scale = sm_count / 148.0;
+        const double resident = sm_count * 4.0 * v[i].blocks;
+        const double nstrips = (n + 32.0 * v[i].K - 1) / (32.0 * v[i].K);
+        const double rate = std::min(v[i].chip * scale, std::min(nstrips, resident) * v[i].lone);
+        if (rate > best * 1.02) { best = rate; bestK = v[i].K; }
     }
     return bestK;
 }
@@ -280,10 +301,13 @@ int Engine::pick_K(int n) const
 // left neighbour (32 steps lane skew + the 32-row publish/fetch granularity).
 // All of them overlap only if a band is at least lag * window steps long;
 // bands are then equalised.
-int Engine::pick_band(int m, int nstrips, int resident) const
+int Engine::pick_band(int m, int nstrips, int resident, int K) const
 {
     if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
-    const long long lag = 128;
+    // rows a strip runs behind its left neighbour: lane skew (32 steps) plus the
+    // publish/fetch granularity (32 steps each way), in rows per step
+    const int rows_per_step = (use_mask_ && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
+    const long long lag = 128LL * rows_per_step;
     const long long window = std::max(1, std::min(resident, nstrips));
     long long target = std::max<long long>(lag * window, 4096);
     if (target >= m) return std::max(32, (m + 31) / 32 * 32);
@@ -307,6 +331,9 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(jobs_.ptr, jobs.data(), sizeof(Job) * (size_t)njobs,
                                       cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
+#ifdef ANYSEQ_PROFILE
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 8, stream_));
+#endif
 
     KernelFn fn = pick_kernel(local, affine, K, use_mask_);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
@@ -315,6 +342,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
+    else nb = default_blocks_per_sm(K, use_mask_, nb);
     long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
 
@@ -414,7 +442,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
     const int resident = resident_warps(K, local, affine);
-    const int band_h = pick_band(m, nstrips, resident);
+    const int band_h = pick_band(m, nstrips, resident, K);
 
     const size_t wpad = (size_t)nstrips * SW;
     if (colH_.ensure(sizeof(int) * (size_t)m) || rowH_.ensure(sizeof(int) * wpad) ||
@@ -466,6 +494,14 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     }
     float ms = 0.f;
     ANYSEQ_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+#ifdef ANYSEQ_PROFILE
+    {
+        const unsigned long long* pc = reinterpret_cast<const unsigned long long*>(h_misc_ + 20);
+        const double nb = (double)pc[3] > 0 ? (double)pc[3] : 1.0;
+        std::fprintf(stderr, "[anyseq profile] K=%d batches=%llu cycles/batch: wait=%.0f io=%.0f steps=%.0f\n", K,
+                     pc[3], pc[0] / nb, pc[1] / nb, pc[2] / nb);
+    }
+#endif
     if (out) {
         out->row_best = h_misc_[kMiscOut + 3];
         out->row_best_j = h_misc_[kMiscOut + 4];

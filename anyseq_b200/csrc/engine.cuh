@@ -101,7 +101,7 @@ private:
                  int* launches);
     int pick_K(int n) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
-    int pick_band(int m, int nstrips, int resident) const;
+    int pick_band(int m, int nstrips, int resident, int K) const;
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

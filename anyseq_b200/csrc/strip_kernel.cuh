@@ -125,38 +125,42 @@ __device__ __forceinline__ int ld_relaxed_sys(const int* p)
 }
 
 // Wait until *flag >= need.  Executed by all lanes of a warp (same address:
-// one transaction).  The poll is a relaxed load (an acquire load costs a
-// CCTL.IVALL -- a whole-L1 invalidate -- per poll); one acquire fence after the
-// condition holds orders the following border loads.  Returns false if the
+// one transaction).  Fast path: one acquire load.  Slow path: relaxed polls (an
+// acquire load costs a CCTL.IVALL -- a whole-L1 invalidate -- per poll), then one
+// acquire load to order the following border loads.  Returns false if the
 // watchdog fired or another warp already reported a failure -- the caller then
 // leaves the kernel, so a logic error shows up as a status code instead of a
 // hung GPU.
 __device__ __forceinline__ bool wait_rows(const int* flag, int need, bool sys, int* status,
                                           unsigned long long timeout_ns)
 {
+    // common case: already published -- a single acquire load
+    int v = sys ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
+    if (v >= need) return true;
     bool ok = true;
-    int v = sys ? ld_relaxed_sys(flag) : ld_relaxed_gpu(flag);
-    if (v < need) {
-        const unsigned long long t0 = global_timer_ns();
-        unsigned spins = 0;
-        while (true) {
-            v = sys ? ld_relaxed_sys(flag) : ld_relaxed_gpu(flag);
-            if (v >= need) break;
-            __nanosleep(200);
-            if ((++spins & 127u) == 0u) {
-                if (*(volatile int*)status != kStatusOk) { ok = false; break; }
-                if (global_timer_ns() - t0 > timeout_ns) {
-                    if (atomicCAS(status, kStatusOk, kStatusTimeout) == kStatusOk) {
-                        status[1] = need; status[2] = v;
-                    }
-                    ok = false;
-                    break;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (true) {
+        v = sys ? ld_relaxed_sys(flag) : ld_relaxed_gpu(flag);
+        if (v >= need) break;
+        ++spins;
+#ifndef ANYSEQ_SPIN_NOSLEEP
+        if (spins > 8u) __nanosleep(spins > 64u ? 400 : 40);
+#endif
+        if ((spins & 127u) == 0u) {
+            if (*(volatile int*)status != kStatusOk) { ok = false; break; }
+            if (global_timer_ns() - t0 > timeout_ns) {
+                if (atomicCAS(status, kStatusOk, kStatusTimeout) == kStatusOk) {
+                    status[1] = need; status[2] = v;
                 }
+                ok = false;
+                break;
             }
         }
     }
-    if (sys) __threadfence_system(); else __threadfence();
-    return __all_sync(kFull, ok);
+    // the poll was relaxed: order the border loads after it
+    v = sys ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
+    return __all_sync(kFull, ok && v >= need);
 }
 
 template <int K>
@@ -233,26 +237,91 @@ struct Cell {
     }
 };
 
-// shared memory of one warp
+// Two rows of one lane per step (R = 2): cell (r0, C) and cell (r1 = r0+1, C),
+// then column C+1.  The two row chains are independent except that row r1 is
+// one column behind row r0 (its F and its diagonal come from the row-r0 cell
+// just relaxed), so a warp carries two dependent chains instead of one: twice
+// the instruction-level parallelism, half the per-cell step overhead, half the
+// lane skew per cell.
+struct StepState2 {
+    int dd0, dd1;        // diag + sigma of the two cells about to be relaxed
+    int e0, e1;          // E to the left, per row
+    int x0, x1;          // X to the left, per row
+    int best;            // LOCAL
+    unsigned mask0, mask1;
+    int qc0, qc1;
+};
+
+template <bool LOCAL, bool AFFINE, int K, bool MASK, int C>
+struct Cell2 {
+    template <int KF, int KS>
+    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState2& s,
+                                               const StepConst& k)
+    {
+        const int up = X[C];
+        const int dd0 = s.dd0, dd1 = s.dd1;
+        if constexpr (C + 1 < K) {
+            if constexpr (MASK) s.dd0 = diag_plus_sigma_mask<C + 1>(s.mask0, up, k.one, k.diff_o, k.same_o);
+            else s.dd0 = diag_plus_sigma(s.qc0, sc[C + 1], up, k.one, k.diff_o, k.same_o);
+        }
+        int h0, h1, x0, x1;
+        if constexpr (AFFINE) {
+            s.e0 = __viaddmax_s32(s.e0, k.ge, s.x0);
+            const int f0 = __viaddmax_s32(F[C], k.ge, up);
+            h0 = LOCAL ? __vimax3_s32_relu(dd0, s.e0, f0) : __vimax3_s32(dd0, s.e0, f0);
+            x0 = imad_add(h0, k.one, k.go);
+            if constexpr (C + 1 < K) {
+                if constexpr (MASK) s.dd1 = diag_plus_sigma_mask<C + 1>(s.mask1, x0, k.one, k.diff_o, k.same_o);
+                else s.dd1 = diag_plus_sigma(s.qc1, sc[C + 1], x0, k.one, k.diff_o, k.same_o);
+            }
+            s.e1 = __viaddmax_s32(s.e1, k.ge, s.x1);
+            const int f1 = __viaddmax_s32(f0, k.ge, x0);
+            h1 = LOCAL ? __vimax3_s32_relu(dd1, s.e1, f1) : __vimax3_s32(dd1, s.e1, f1);
+            x1 = imad_add(h1, k.one, k.go);
+            F[C] = f1;
+        } else {
+            const int t0 = max(s.x0, up);
+            h0 = LOCAL ? __viaddmax_s32_relu(t0, k.ge, dd0) : __viaddmax_s32(t0, k.ge, dd0);
+            x0 = h0;
+            if constexpr (C + 1 < K) {
+                if constexpr (MASK) s.dd1 = diag_plus_sigma_mask<C + 1>(s.mask1, x0, k.one, k.diff_o, k.same_o);
+                else s.dd1 = diag_plus_sigma(s.qc1, sc[C + 1], x0, k.one, k.diff_o, k.same_o);
+            }
+            const int t1 = max(s.x1, x0);
+            h1 = LOCAL ? __viaddmax_s32_relu(t1, k.ge, dd1) : __viaddmax_s32(t1, k.ge, dd1);
+            x1 = h1;
+        }
+        if constexpr (LOCAL) s.best = __vimax3_s32(s.best, h0, h1);
+        X[C] = x1;
+        s.x0 = x0;
+        s.x1 = x1;
+        if constexpr (C + 1 < K) Cell2<LOCAL, AFFINE, K, MASK, C + 1>::run(X, F, sc, s, k);
+    }
+};
+
+// shared memory of one warp (sized for R = 2 rows per step, 32 steps per batch)
 struct WarpSmem {
-    int2 in[32];        // left border rows of the current 32-row batch (X form, E)
-    int2 out[64];       // right edge rows waiting to be published (ring)
-    uint8_t q[64];      // query symbols (MASK: codes) of the last 64 rows (ring)
+    int2 in[64];        // left border rows of the current batch (X form, E)
+    int2 out[128];      // right edge rows waiting to be published (ring)
+    uint8_t q[128];     // query symbols (MASK: codes) of the last 128 rows (ring)
 };
 
 // One (band, strip) item.  PARTIAL = the strip is cut by the right matrix edge
 // (only the last strip of a job can be): the columns past the edge compute
 // don't-care values (dependencies only run left->right, so they never reach a
 // valid cell), the edge column is picked out for the output, and the local
-// maximum is masked.
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK>
+// maximum is masked.  R = rows per lane and step (PARTIAL items use R = 1).
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
                                              const KernelArgs& a, WarpSmem& sm,
                                              unsigned* __restrict__ s_mask /* [ncodes][32] */,
                                              const uint8_t* __restrict__ s_lut /* [2][256] */,
                                              const int lane)
 {
+    static_assert(R == 1 || (R == 2 && !PARTIAL), "two-row tiles are not used for partial strips");
     constexpr int SW = kWarp * K;
+    constexpr int BR = 32 * R;             // rows per batch
+    constexpr int QM = 64 * R - 1;         // ring masks
     const int i0 = band * J.band_h;
     const int hb = min(J.band_h, J.h - i0);
     const int j0 = strip * SW;
@@ -328,24 +397,21 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     const int outlane = PARTIAL ? (wv - 1) / K : 31;
     k.outc = PARTIAL ? (wv - 1) % K : K - 1;
     k.nvalid = PARTIAL ? max(0, min(K, wv - lane * K)) : K;
-    const int T = hb + outlane;            // number of steps
-    int hr = 0, er = 0;
-    int flushed = 0;
+    const int ngroups = (hb + R - 1) / R;  // row groups of R rows
+    const int T = ngroups + outlane;       // number of steps
+    int hr[R], er[R];
+    unsigned mask_cur[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { hr[r] = 0; er[r] = 0; mask_cur[r] = 0u; }
+    int flushed = 0;                       // rows published so far
     StepState st;
-    st.dd = 0;
-    st.e = 0;
-    st.xleft = 0;
-    st.best = kScoreMin;
-    st.hprev = kScoreMin;
-    st.es = 0;
-    st.mask = 0u;
-    st.qc = 0;
+    st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.mask = 0u; st.qc = 0;
 
     auto flush32 = [&](int base) {
         // rows [base, base+32) of the out lane's edge -> colH/colE (coalesced)
         const int r = base + lane;
         if (r < hb) {
-            const int2 v = sm.out[r & 63];
+            const int2 v = sm.out[r & QM];
             __stcg(J.colH + i0 + r, v.x - go);
             if constexpr (AFFINE) __stcg(J.colE + i0 + r, v.y);
             if (mirror) {
@@ -366,54 +432,111 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         }
     };
     // MASK: column mask of row i (its query code selects one of the lane's masks)
-    auto row_mask = [&](int i) -> unsigned { return s_mask[(int)sm.q[i & 63] * 32 + lane]; };
+    auto row_mask = [&](int i) -> unsigned { return s_mask[(int)sm.q[i & QM] * 32 + lane]; };
 
-    // one anti-diagonal step; GUARD = some lanes may be outside [0, hb)
+    // one row of one lane (R = 1 chain): used for R = 1 and for the guarded steps of R = 2
+    auto relax_row = [&](const int row, const int xl, const int el, const unsigned mask, int& hro, int& ero) {
+        if constexpr (MASK) {
+            st.mask = mask;
+            st.dd = diag_plus_sigma_mask<0>(mask, dcarry, k.one, k.diff_o, k.same_o);
+        } else {
+            st.qc = sm.q[row & QM];
+            st.dd = diag_plus_sigma(st.qc, sc[0], dcarry, k.one, k.diff_o, k.same_o);
+        }
+        dcarry = xl;
+        st.xleft = xl;
+        st.e = el;
+        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, 0>::run(X, F, sc, st, k);
+        hro = st.xleft;
+        ero = st.e;
+        if constexpr (PARTIAL) {
+            if (lane == outlane) {
+                int hs = X[0];
+#pragma unroll
+                for (int c = 1; c < K; ++c)
+                    if (c == k.outc) hs = X[c];
+                sm.out[row & QM] = make_int2(hs, st.es);
+            }
+        } else {
+            if (lane == 31) sm.out[row & QM] = make_int2(hro, ero);
+        }
+    };
+
+    // one anti-diagonal step; GUARD = some rows of some lanes may be outside [0, hb)
     auto step = [&](auto guard_tag, const int t) {
         constexpr bool GUARD = decltype(guard_tag)::value;
-        int xl = __shfl_up_sync(kFull, hr, 1);
-        int el = 0;
-        if constexpr (AFFINE) el = __shfl_up_sync(kFull, er, 1);
-        const int2 bnd = sm.in[t & 31];
-        if (lane == 0) { xl = bnd.x; el = bnd.y; }
-        const int i = t - lane;
-        unsigned mask_next = 0u;
-        if constexpr (MASK) mask_next = row_mask(i + 1);      // prefetch, off the critical path
-        if (!GUARD || (unsigned)i < (unsigned)hb) {
-            if constexpr (MASK) {
-                st.dd = diag_plus_sigma_mask<0>(st.mask, dcarry, k.one, k.diff_o, k.same_o);
-            } else {
-                st.qc = sm.q[i & 63];
-                st.dd = diag_plus_sigma(st.qc, sc[0], dcarry, k.one, k.diff_o, k.same_o);
-            }
-            dcarry = xl;
-            st.xleft = xl;
-            st.e = el;
-            Cell<LOCAL, AFFINE, K, PARTIAL, MASK, 0>::run(X, F, sc, st, k);
-            hr = st.xleft;
-            er = st.e;
-            if constexpr (PARTIAL) {
-                if (lane == outlane) {
-                    int hs = X[0];
+        int xl[R], el[R];
 #pragma unroll
-                    for (int c = 1; c < K; ++c)
-                        if (c == k.outc) hs = X[c];
-                    sm.out[i & 63] = make_int2(hs, st.es);
-                }
+        for (int r = 0; r < R; ++r) {
+            xl[r] = __shfl_up_sync(kFull, hr[r], 1);
+            el[r] = 0;
+            if constexpr (AFFINE) el[r] = __shfl_up_sync(kFull, er[r], 1);
+        }
+        if constexpr (R == 1) {
+            const int2 bnd = sm.in[t & 31];
+            if (lane == 0) { xl[0] = bnd.x; el[0] = bnd.y; }
+        } else {
+            const int4 bnd = *reinterpret_cast<const int4*>(&sm.in[2 * (t & 31)]);
+            if (lane == 0) { xl[0] = bnd.x; el[0] = bnd.y; xl[1] = bnd.z; el[1] = bnd.w; }
+        }
+        const int g = t - lane;                 // row group of this lane
+        unsigned mask_next[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            mask_next[r] = 0u;
+            if constexpr (MASK) mask_next[r] = row_mask(R * (g + 1) + r);   // prefetch, off the critical path
+        }
+        if constexpr (!GUARD && R == 2) {
+            StepState2 s2;
+            s2.best = st.best;
+            s2.mask0 = mask_cur[0];
+            s2.mask1 = mask_cur[1];
+            s2.qc0 = 0; s2.qc1 = 0;
+            if constexpr (MASK) {
+                s2.dd0 = diag_plus_sigma_mask<0>(s2.mask0, dcarry, k.one, k.diff_o, k.same_o);
+                s2.dd1 = diag_plus_sigma_mask<0>(s2.mask1, xl[0], k.one, k.diff_o, k.same_o);
             } else {
-                if (lane == 31) sm.out[i & 63] = make_int2(hr, er);
+                s2.qc0 = sm.q[(2 * g) & QM];
+                s2.qc1 = sm.q[(2 * g + 1) & QM];
+                s2.dd0 = diag_plus_sigma(s2.qc0, sc[0], dcarry, k.one, k.diff_o, k.same_o);
+                s2.dd1 = diag_plus_sigma(s2.qc1, sc[0], xl[0], k.one, k.diff_o, k.same_o);
+            }
+            dcarry = xl[R - 1];
+            s2.x0 = xl[0]; s2.e0 = el[0];
+            s2.x1 = xl[R - 1]; s2.e1 = el[R - 1];
+            Cell2<LOCAL, AFFINE, K, MASK, 0>::run(X, F, sc, s2, k);
+            hr[0] = s2.x0; er[0] = s2.e0;
+            hr[R - 1] = s2.x1; er[R - 1] = s2.e1;
+            st.best = s2.best;
+            if (lane == 31)
+                *reinterpret_cast<int4*>(&sm.out[(2 * g) & QM]) = make_int4(s2.x0, s2.e0, s2.x1, s2.e1);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = R * g + r;
+                if (!GUARD || (unsigned)row < (unsigned)hb) relax_row(row, xl[r], el[r], mask_cur[r], hr[r], er[r]);
             }
         }
         // also on steps where this lane is still above the band: its first row
         // must find the mask of row 0 in place
-        if constexpr (MASK) st.mask = mask_next;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mask_cur[r] = mask_next[r];
     };
 
+#ifdef ANYSEQ_PROFILE
+    long long pf_wait = 0, pf_io = 0, pf_steps = 0, pf_t;
+#define PF_BEGIN() pf_t = clock64()
+#define PF_END(acc) acc += clock64() - pf_t
+#else
+#define PF_BEGIN()
+#define PF_END(acc)
+#endif
     for (int tb = 0; tb < T; tb += 32) {
         __syncwarp();
+        PF_BEGIN();
         // (1) publish the edge rows the out lane finished so far
         {
-            const int completed = min(max(tb - outlane, 0), hb);
+            const int completed = min(max(R * (tb - outlane), 0), hb);
             bool any = false;
             while (completed - flushed >= 32) {
                 flush32(flushed);
@@ -422,29 +545,40 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             }
             if (any && flushed < hb) publish(i0 + flushed);   // the final publish is below
         }
-        // (2) fetch the next 32 rows of the left border and of the query
+        // (2) fetch the next batch of rows of the left border and of the query
         {
-            const int r = tb + lane;
-            int2 v = make_int2(0, kNegInf);
-            uint8_t qv = 0;
-            if (tb < hb) {
-                if (lflag != nullptr) {
-                    if (!wait_rows(lflag, i0 + min(tb + 32, hb), lsys, status, timeout_ns)) return false;
-                }
+            const int rb = R * tb;              // first row of the batch
+            PF_END(pf_io);
+            PF_BEGIN();
+            if (rb < hb && lflag != nullptr) {
+                if (!wait_rows(lflag, i0 + min(rb + BR, hb), lsys, status, timeout_ns)) return false;
+            }
+            PF_END(pf_wait);
+            PF_BEGIN();
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int r = rb + 32 * u + lane;
+                int2 v = make_int2(0, kNegInf);
+                uint8_t qv = 0;
                 if (r < hb) {
                     v.x = __ldcg(linH + r) + go;
                     if constexpr (AFFINE) v.y = __ldcg(linE + r);
                     qv = MASK ? s_lut[qrow[r]] : qrow[r];
                 }
+                sm.in[32 * u + lane] = v;
+                sm.q[r & QM] = qv;
             }
-            sm.in[lane] = v;
-            sm.q[r & 63] = qv;
             __syncwarp();
-            if constexpr (MASK) st.mask = row_mask(tb - lane);   // row of this lane at step tb
+            if constexpr (MASK) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) mask_cur[r] = row_mask(R * (tb - lane) + r);   // rows of this lane at step tb
+            }
         }
-        // (3) 32 anti-diagonal steps; batches in which every lane is inside the
-        //     band run the unguarded body
-        if (tb >= 31 && tb + 32 <= hb) {
+        PF_END(pf_io);
+        PF_BEGIN();
+        // (3) 32 anti-diagonal steps; batches in which every row of every lane is
+        //     inside the band run the unguarded body
+        if (tb >= 31 && R * (tb + 32) <= hb) {
 #pragma unroll 1
             for (int t = tb; t < tb + 32; ++t) step(std::false_type{}, t);
         } else {
@@ -452,7 +586,17 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #pragma unroll 1
             for (int t = tb; t < tend; ++t) step(std::true_type{}, t);
         }
+        PF_END(pf_steps);
     }
+#ifdef ANYSEQ_PROFILE
+    if (lane == 0) {
+        unsigned long long* pc = reinterpret_cast<unsigned long long*>(a.status + 20);
+        atomicAdd(pc + 0, (unsigned long long)pf_wait);
+        atomicAdd(pc + 1, (unsigned long long)pf_io);
+        atomicAdd(pc + 2, (unsigned long long)pf_steps);
+        atomicAdd(pc + 3, (unsigned long long)((T + 31) / 32));
+    }
+#endif
 
     // drain: remaining edge rows, bottom border, corner, local maximum
     __syncwarp();
@@ -470,6 +614,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     if (lane == 0) __stcg(J.corner + strip, dcarry - go);
     if constexpr (LOCAL) {
         int best = st.best;
+        if constexpr (!PARTIAL) best = max(best, st.hprev);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
         if (lane == 0) atomicMax(J.best, best);
@@ -489,9 +634,19 @@ constexpr int strip_min_blocks()
     return K >= 32 ? (MASK ? ANYSEQ_K32_MASK_BLOCKS : 4) : (K >= 16 ? 5 : 6);
 }
 
+// rows per lane and step: two-row tiles for the wide MASK kernels
+#ifndef ANYSEQ_ROWS_WIDE
+#define ANYSEQ_ROWS_WIDE 2
+#endif
+template <int K, bool MASK>
+struct StripRows {
+    static constexpr int value = (MASK && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
+};
+
 template <bool LOCAL, bool AFFINE, int K, bool MASK>
 __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_kernel(const KernelArgs a)
 {
+    constexpr int R = StripRows<K, MASK>::value;
     __shared__ WarpSmem s_warp[kWarpsPerBlock];
     __shared__ uint8_t s_lut[MASK ? 512 : 4];
     extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32] column masks
@@ -509,8 +664,7 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
     unsigned* s_mask = s_dyn + warp * a.ncodes * 32;
     // the query ring is read one row ahead (mask prefetch): never let an
     // uninitialised byte be used as a code
-    s_warp[warp].q[lane] = 0;
-    s_warp[warp].q[32 + lane] = 0;
+    for (int x = lane; x < 128; x += 32) s_warp[warp].q[x] = 0;
     __syncwarp();
 
     // Items are claimed in index order from a global counter (the first round is
@@ -527,9 +681,9 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)
-            ok = process_item<LOCAL, AFFINE, K, true, MASK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, true, MASK, 1>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         else
-            ok = process_item<LOCAL, AFFINE, K, false, MASK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, false, MASK, R>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         if (!ok) return;
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(a.next_item, 1ull);

@@ -317,7 +317,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
                 J.h = len;
                 J.w = w;
                 J.nstrips = (w + SW - 1) / SW;
-                J.band_h = pick_band(len, J.nstrips, resident);
+                J.band_h = pick_band(len, J.nstrips, resident, K);
                 J.nbands = (len + J.band_h - 1) / J.band_h;
                 J.colH = (side == 0 ? colH_.as<int>() : colH2_.as<int>()) + off;
                 J.rowH = rowH_.as<int>() + c0;
