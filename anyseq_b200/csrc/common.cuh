@@ -31,13 +31,18 @@ enum StatusCode : int {
 //
 // Boundary storage mirrors the reference's O(m+n) scheme (column vector, row
 // vector, corners: src/scoring.impala:218-259), re-laid for streaming:
-//   colH/colE[h]  strip x reads rows from it (written by strip x-1 or the init
-//                 kernel) and overwrites them with its own right edge.
+//   col[h]        one 16-byte BORDER RECORD per row: {H, tag, E, tag}.  Strip x
+//                 consumes the records tagged x (tag 0 = the matrix border,
+//                 written by the init kernel) and overwrites them with its own
+//                 right edge tagged x+1.  Data and tag share an 8-byte word
+//                 (stored atomically), so a consumer that sees the tag has the
+//                 value: no flag, no fence, and the next batch of records can be
+//                 prefetched speculatively (the NCCL "LL" protocol idea).
 //   rowH/rowF[w'] item (b,x) loads its top border from it and stores its
 //                 bottom border back (w' = w rounded up to the strip width).
 //   corner[x]     H(i0-1, j0-1) for the next band of strip x.
-//   progress[x]   number of rows of strip x whose right edge is published
-//                 (monotone over bands) -- the only synchronisation.
+//   progress[x]   rows of strip x completed band-wise (release/acquire): only
+//                 the band hand-over (once per item) uses it.
 struct Job {
     const uint8_t* q;
     const uint8_t* s;
@@ -45,22 +50,20 @@ struct Job {
     int band_h;
     int nstrips, nbands;
     long long item_begin;    // prefix sum of nstrips*nbands over jobs
-    int* colH;
-    int* colE;
+    int4* col;
     int* rowH;
     int* rowF;
     int* corner;
     int* progress;
     int* best;               // local mode: running maximum (atomicMax)
-    // multi-GPU chaining (null on a single GPU): strip 0 reads its left border
-    // from inH/inE once *in_progress >= rows; the last strip additionally
-    // mirrors its right edge to outH/outE (peer memory) and *out_progress.
-    const int* inH;
-    const int* inE;
-    const int* in_progress;
-    int* outH;
-    int* outE;
-    int* out_progress;
+    // multi-GPU chaining (null on a single GPU): strip 0 consumes the records
+    // tagged in_tag from `in` (this rank's inbox, written by the previous rank
+    // over NVLink); the last strip mirrors its right edge into `out` (the next
+    // rank's inbox, peer memory) tagged out_tag.
+    const int4* in;
+    int4* out;
+    int in_tag;
+    int out_tag;
     // initialisation of the borders (init kernel)
     int init_global;         // 1: gap multiples (global), 0: zeros
 };

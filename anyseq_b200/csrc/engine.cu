@@ -26,8 +26,8 @@ __global__ void init_jobs_kernel(const Job* __restrict__ jobs, int njobs, ScoreP
         const int n = max(max(J.h, wpad), J.nstrips);
         for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
             if (idx < J.h) {
-                J.colH[idx] = J.init_global ? sp.gap_open + idx * sp.gap_extend : 0;
-                if (J.colE) J.colE[idx] = kNegInf;
+                // left matrix border as records tagged 0: {H(idx,-1), 0, E(idx,-1) = -inf, 0}
+                J.col[idx] = make_int4(J.init_global ? sp.gap_open + idx * sp.gap_extend : 0, 0, kNegInf, 0);
             }
             if (idx < wpad) {
                 J.rowH[idx] = J.init_global ? sp.gap_open + (col0 + idx) * sp.gap_extend : 0;
@@ -49,13 +49,13 @@ __global__ void init_jobs_kernel(const Job* __restrict__ jobs, int njobs, ScoreP
 // index attaining the maximum (src/utils.impala:30-49,
 // src/iteration_cpu.impala:205-250); arg_max_lowest reproduces that.
 // ---------------------------------------------------------------------------
-__device__ void arg_max_lowest(const int* __restrict__ v, int n, int& best, int& best_i)
+__device__ void arg_max_lowest(const int* __restrict__ v, int n, int stride, int& best, int& best_i)
 {
     __shared__ int s_v[32];
     __shared__ int s_i[32];
     int bv = kScoreMin, bi = 0x7fffffff;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int x = __ldcg(v + i);
+        const int x = __ldcg(v + (size_t)i * stride);
         if (x > bv) { bv = x; bi = i; }   // ascending i per thread: first max kept
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -87,13 +87,14 @@ __global__ void finish_score_kernel(const Job* __restrict__ jobs, int mode, int 
 {
     const Job J = jobs[0];
     int rv, ri, cv, ci;
-    arg_max_lowest(J.rowH, J.w, rv, ri);
-    arg_max_lowest(J.colH, J.h, cv, ci);
+    const int* colH = reinterpret_cast<const int*>(J.col);      // .x of every 16-byte record
+    arg_max_lowest(J.rowH, J.w, 1, rv, ri);
+    arg_max_lowest(colH, J.h, 4, cv, ci);
     if (threadIdx.x == 0) {
         out[3] = rv; out[4] = ri + col0; out[5] = cv; out[6] = ci;
-        out[7] = __ldcg(J.colH + J.h - 1);
+        out[7] = __ldcg(colH + 4 * (size_t)(J.h - 1));
         if (mode == kGlobal) {
-            out[0] = __ldcg(J.colH + J.h - 1);
+            out[0] = __ldcg(colH + 4 * (size_t)(J.h - 1));
             out[1] = J.h - 1; out[2] = n_total - 1;
         } else if (mode == kSemiglobal) {
             // candidates -1 (value init = 0) come first and win ties
@@ -126,7 +127,8 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask)
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)
 static int rows_per_step(int K, bool mask)
 {
-    return (mask && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
+    if (!mask) return 1;
+    return K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1);
 }
 
 // CTAs per SM actually launched.  Two-row tiles carry two dependent chains per
@@ -136,7 +138,9 @@ static int rows_per_step(int K, bool mask)
 static int default_blocks_per_sm(int K, bool mask, int occupancy_max)
 {
     int nb = occupancy_max;
-    if (rows_per_step(K, mask) == 2) nb = std::min(nb, K >= 32 ? 2 : 3);
+    const int R = rows_per_step(K, mask);
+    if (R >= 4) nb = std::min(nb, 1);
+    else if (R == 2) nb = std::min(nb, K >= 32 ? 2 : 3);
     return nb;
 }
 
@@ -226,8 +230,8 @@ int Engine::init(int dev)
 void Engine::destroy()
 {
     if (device >= 0) cudaSetDevice(device);
-    DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &colH_, &colE_, &rowH_, &rowF_, &corner_,
-                            &progress_, &jobs_, &misc_, &lut_, &colH2_, &colE2_, &aux_, &aux2_, &pred_,
+    DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
+                            &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
                             &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_};
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
@@ -304,10 +308,9 @@ int Engine::pick_K(int n) const
 int Engine::pick_band(int m, int nstrips, int resident, int K) const
 {
     if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
-    // rows a strip runs behind its left neighbour: lane skew (32 steps) plus the
-    // publish/fetch granularity (32 steps each way), in rows per step
-    const int rows_per_step = (use_mask_ && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
-    const long long lag = 128LL * rows_per_step;
+    // rows a strip runs behind its left neighbour: lane skew (32 steps of R rows)
+    // plus the 32-row publish and fetch batches, plus slack
+    const long long lag = 32LL * rows_per_step(K, use_mask_) + 96;
     const long long window = std::max(1, std::min(resident, nstrips));
     long long target = std::max<long long>(lag * window, 4096);
     if (target >= m) return std::max(32, (m + 31) / 32 * 32);
@@ -332,7 +335,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
                                       cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
 #ifdef ANYSEQ_PROFILE
-    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 8, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
 #endif
 
     KernelFn fn = pick_kernel(local, affine, K, use_mask_);
@@ -445,11 +448,10 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int band_h = pick_band(m, nstrips, resident, K);
 
     const size_t wpad = (size_t)nstrips * SW;
-    if (colH_.ensure(sizeof(int) * (size_t)m) || rowH_.ensure(sizeof(int) * wpad) ||
+    if (col_.ensure(sizeof(int4) * (size_t)m) || rowH_.ensure(sizeof(int) * wpad) ||
         corner_.ensure(sizeof(int) * (size_t)nstrips) || progress_.ensure(sizeof(int) * (size_t)nstrips))
         return ANYSEQ_ERR_NO_DEVICE;
-    if (affine && (colE_.ensure(sizeof(int) * (size_t)m) || rowF_.ensure(sizeof(int) * wpad)))
-        return ANYSEQ_ERR_NO_DEVICE;
+    if (affine && rowF_.ensure(sizeof(int) * wpad)) return ANYSEQ_ERR_NO_DEVICE;
 
     Job J;
     std::memset(&J, 0, sizeof(J));
@@ -460,16 +462,16 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     J.band_h = band_h;
     J.nstrips = nstrips;
     J.nbands = (m + band_h - 1) / band_h;
-    J.colH = colH_.as<int>();
-    J.colE = affine ? colE_.as<int>() : nullptr;
+    J.col = col_.as<int4>();
     J.rowH = rowH_.as<int>();
     J.rowF = affine ? rowF_.as<int>() : nullptr;
     J.corner = corner_.as<int>();
     J.progress = progress_.as<int>();
     J.best = misc_.as<int>() + kMiscBest;
     J.init_global = sc.mode == ANYSEQ_GLOBAL;
-    if (inbox) { J.inH = inbox->H(); J.inE = inbox->E(); J.in_progress = inbox->progress(); }
-    if (next_inbox) { J.outH = next_inbox->H(); J.outE = next_inbox->E(); J.out_progress = next_inbox->progress(); }
+    // the tag of a run is agreed without communication: both ends count their uses of the inbox
+    if (inbox) { J.in = inbox->records; J.in_tag = 0x40000000 + (++inbox->uses_in & 0xffffff); }
+    if (next_inbox) { J.out = next_inbox->records; J.out_tag = 0x40000000 + (++next_inbox->uses_out & 0xffffff); }
 
     std::vector<Job> jobs(1, J);
     int launches = 0;
@@ -498,8 +500,9 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     {
         const unsigned long long* pc = reinterpret_cast<const unsigned long long*>(h_misc_ + 20);
         const double nb = (double)pc[3] > 0 ? (double)pc[3] : 1.0;
-        std::fprintf(stderr, "[anyseq profile] K=%d batches=%llu cycles/batch: wait=%.0f io=%.0f steps=%.0f\n", K,
-                     pc[3], pc[0] / nb, pc[1] / nb, pc[2] / nb);
+        std::fprintf(stderr, "[anyseq profile] K=%d batches=%llu cycles/batch: wait=%.0f io=%.0f steps=%.0f | items=%llu "
+                             "cycles/item: bandwait=%.0f total=%.0f\n", K, pc[3], pc[0] / nb, pc[1] / nb, pc[2] / nb, pc[6],
+                     pc[6] ? (double)pc[4] / pc[6] : 0.0, pc[6] ? (double)pc[5] / pc[6] : 0.0);
     }
 #endif
     if (out) {

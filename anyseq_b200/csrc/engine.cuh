@@ -49,17 +49,16 @@ enum MiscWord : int {
     kMiscBest = 4,       // local running maximum
     kMiscOut = 8,        // 8 words: finish kernel output
     kMiscCounter = 16,   // 2 words (8-byte aligned): work-item counter of the strip kernel
-    kMiscWords = 32
+    kMiscWords = 40
 };
 
-struct Inbox {            // left-border mailbox of a rank (multi-GPU wavefront)
-    int* base = nullptr;  // [0..63] header (word 0 = progress), then H[rows], E[rows]
+struct Inbox {            // left-border mailbox of a rank (multi-GPU wavefront): one 16-byte record per row
+    int4* records = nullptr;
     int rows = 0;
     bool owned = false;   // false: opened from a peer's IPC handle
-    int* progress() const { return base; }
-    int* H() const { return base + 64; }
-    int* E() const { return base + 64 + ((rows + 63) / 64) * 64; }
-    static size_t bytes_for(int rows) { return sizeof(int) * (64 + 2 * (size_t)((rows + 63) / 64) * 64); }
+    int uses_in = 0;      // runs that consumed from it (this process)
+    int uses_out = 0;     // runs that produced into it (this process)
+    static size_t bytes_for(int rows) { return sizeof(int4) * (size_t)rows + 256; }
 };
 
 class Engine {
@@ -106,9 +105,9 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     DeviceBuffer seq_q_, seq_s_, seq_qr_, seq_sr_;
-    DeviceBuffer colH_, colE_, rowH_, rowF_, corner_, progress_, jobs_, misc_;
+    DeviceBuffer col_, rowH_, rowF_, corner_, progress_, jobs_, misc_;
     DeviceBuffer lut_;                // byte -> code tables of the MASK kernels + presence bits
-    DeviceBuffer colH2_, colE2_;      // second column set (Hirschberg right halves)
+    DeviceBuffer col2_;               // second column-record set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
     int* h_misc_ = nullptr;           // pinned mirror of misc_

@@ -2,8 +2,9 @@
 // (SURVEY.md 8e).  A rank allocates its inbox in its own HBM and exports it as
 // a CUDA IPC handle; the producing rank (previous column strip, another
 // process on another GPU of the same NVSwitch domain) opens the handle and its
-// strip kernel stores the right-edge rows + the progress counter straight into
-// it over NVLink (st.global on the peer mapping, fence.sys + st.relaxed.sys).
+// strip kernel stores its right-edge rows straight into it over NVLink as tagged
+// 16-byte records {H, tag, E, tag} (plain st.global on the peer mapping; data and
+// tag share an 8-byte word, so no fence and no separate flag are needed).
 #include "engine.cuh"
 
 #include <cstring>
@@ -20,8 +21,8 @@ int Engine::inbox_create(int rows, Inbox** out, void* handle64)
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, Inbox::bytes_for(rows));
     if (e != cudaSuccess) { delete b; ANYSEQ_CUDA_CHECK(e); }
-    b->base = static_cast<int*>(p);
-    e = cudaMemset(p, 0, 64 * sizeof(int));
+    b->records = static_cast<int4*>(p);
+    e = cudaMemset(p, 0, Inbox::bytes_for(rows));
     if (e != cudaSuccess) { cudaFree(p); delete b; ANYSEQ_CUDA_CHECK(e); }
     if (handle64) {
         cudaIpcMemHandle_t h;
@@ -45,7 +46,7 @@ int Engine::inbox_open(const void* handle64, int rows, Inbox** out)
     Inbox* b = new Inbox();
     b->rows = rows;
     b->owned = false;
-    b->base = static_cast<int*>(p);
+    b->records = static_cast<int4*>(p);
     *out = b;
     return ANYSEQ_OK;
 }
@@ -54,9 +55,14 @@ int Engine::inbox_reset(Inbox* box)
 {
     std::lock_guard<std::recursive_mutex> lock(mu_);
     ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
-    if (!box->owned) { set_last_error("only the owning rank resets an inbox"); return ANYSEQ_ERR_BAD_ARG; }
-    ANYSEQ_CUDA_CHECK(cudaMemset(box->base, 0, 64 * sizeof(int)));
-    ANYSEQ_CUDA_CHECK(cudaDeviceSynchronize());
+    // records carry a per-run tag, so nothing has to be cleared between runs; a reset
+    // only re-synchronises the run counters of the two ends (both must call it)
+    box->uses_in = 0;
+    box->uses_out = 0;
+    if (box->owned) {
+        ANYSEQ_CUDA_CHECK(cudaMemset(box->records, 0, Inbox::bytes_for(box->rows)));
+        ANYSEQ_CUDA_CHECK(cudaDeviceSynchronize());
+    }
     return ANYSEQ_OK;
 }
 
@@ -64,10 +70,10 @@ void Engine::inbox_destroy(Inbox* box)
 {
     std::lock_guard<std::recursive_mutex> lock(mu_);
     cudaSetDevice(device);
-    if (!box->base) return;
-    if (box->owned) cudaFree(box->base);
-    else cudaIpcCloseMemHandle(box->base);
-    box->base = nullptr;
+    if (!box->records) return;
+    if (box->owned) cudaFree(box->records);
+    else cudaIpcCloseMemHandle(box->records);
+    box->records = nullptr;
 }
 
 }  // namespace anyseq

@@ -237,74 +237,98 @@ struct Cell {
     }
 };
 
-// Two rows of one lane per step (R = 2): cell (r0, C) and cell (r1 = r0+1, C),
-// then column C+1.  The two row chains are independent except that row r1 is
-// one column behind row r0 (its F and its diagonal come from the row-r0 cell
-// just relaxed), so a warp carries two dependent chains instead of one: twice
-// the instruction-level parallelism, half the per-cell step overhead, half the
-// lane skew per cell.
-struct StepState2 {
-    int dd0, dd1;        // diag + sigma of the two cells about to be relaxed
-    int e0, e1;          // E to the left, per row
-    int x0, x1;          // X to the left, per row
+// R rows of one lane per step (R = 2 or 4): cells (r, C) for r = 0..R-1, then
+// column C+1.  Row r is one column behind row r-1 (its F and its diagonal come
+// from the row r-1 cell just relaxed), so a lane carries R dependent chains in a
+// small 2-D wavefront instead of one chain: R times the instruction-level
+// parallelism, 1/R of the per-cell step overhead, and one such warp per
+// scheduler is enough to keep the issue slots busy.
+template <int R>
+struct StepStateR {
+    int dd[R];           // diag + sigma of the R cells about to be relaxed
+    int e[R];            // E to the left, per row
+    int x[R];            // X to the left, per row
+    unsigned mask[R];    // MASK: column masks of the R rows
+    int qc[R];           // !MASK: query bytes of the R rows
     int best;            // LOCAL
-    unsigned mask0, mask1;
-    int qc0, qc1;
+    int xs[R], es[R];    // PARTIAL: X and E of the edge column, per row
 };
 
-template <bool LOCAL, bool AFFINE, int K, bool MASK, int C>
-struct Cell2 {
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, int C>
+struct CellR {
     template <int KF, int KS>
-    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState2& s,
+    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepStateR<R>& s,
                                                const StepConst& k)
     {
-        const int up = X[C];
-        const int dd0 = s.dd0, dd1 = s.dd1;
-        if constexpr (C + 1 < K) {
-            if constexpr (MASK) s.dd0 = diag_plus_sigma_mask<C + 1>(s.mask0, up, k.one, k.diff_o, k.same_o);
-            else s.dd0 = diag_plus_sigma(s.qc0, sc[C + 1], up, k.one, k.diff_o, k.same_o);
-        }
-        int h0, h1, x0, x1;
-        if constexpr (AFFINE) {
-            s.e0 = __viaddmax_s32(s.e0, k.ge, s.x0);
-            const int f0 = __viaddmax_s32(F[C], k.ge, up);
-            h0 = LOCAL ? __vimax3_s32_relu(dd0, s.e0, f0) : __vimax3_s32(dd0, s.e0, f0);
-            x0 = imad_add(h0, k.one, k.go);
+        int above_x = X[C];                      // X of the cell above (row -1 of this group: the stored row)
+        int above_f = 0;
+        if constexpr (AFFINE) above_f = F[C];
+        int hrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int dd = s.dd[r];
             if constexpr (C + 1 < K) {
-                if constexpr (MASK) s.dd1 = diag_plus_sigma_mask<C + 1>(s.mask1, x0, k.one, k.diff_o, k.same_o);
-                else s.dd1 = diag_plus_sigma(s.qc1, sc[C + 1], x0, k.one, k.diff_o, k.same_o);
+                // diagonal term of cell (r, C+1): H(r-1, C) = the cell above this one
+                if constexpr (MASK) s.dd[r] = diag_plus_sigma_mask<C + 1>(s.mask[r], above_x, k.one, k.diff_o, k.same_o);
+                else s.dd[r] = diag_plus_sigma(s.qc[r], sc[C + 1], above_x, k.one, k.diff_o, k.same_o);
             }
-            s.e1 = __viaddmax_s32(s.e1, k.ge, s.x1);
-            const int f1 = __viaddmax_s32(f0, k.ge, x0);
-            h1 = LOCAL ? __vimax3_s32_relu(dd1, s.e1, f1) : __vimax3_s32(dd1, s.e1, f1);
-            x1 = imad_add(h1, k.one, k.go);
-            F[C] = f1;
-        } else {
-            const int t0 = max(s.x0, up);
-            h0 = LOCAL ? __viaddmax_s32_relu(t0, k.ge, dd0) : __viaddmax_s32(t0, k.ge, dd0);
-            x0 = h0;
-            if constexpr (C + 1 < K) {
-                if constexpr (MASK) s.dd1 = diag_plus_sigma_mask<C + 1>(s.mask1, x0, k.one, k.diff_o, k.same_o);
-                else s.dd1 = diag_plus_sigma(s.qc1, sc[C + 1], x0, k.one, k.diff_o, k.same_o);
+            int h, x;
+            if constexpr (AFFINE) {
+                s.e[r] = __viaddmax_s32(s.e[r], k.ge, s.x[r]);
+                const int f = __viaddmax_s32(above_f, k.ge, above_x);
+                h = LOCAL ? __vimax3_s32_relu(dd, s.e[r], f) : __vimax3_s32(dd, s.e[r], f);
+                x = imad_add(h, k.one, k.go);
+                above_f = f;
+            } else {
+                const int t = max(s.x[r], above_x);
+                h = LOCAL ? __viaddmax_s32_relu(t, k.ge, dd) : __viaddmax_s32(t, k.ge, dd);
+                x = h;
             }
-            const int t1 = max(s.x1, x0);
-            h1 = LOCAL ? __viaddmax_s32_relu(t1, k.ge, dd1) : __viaddmax_s32(t1, k.ge, dd1);
-            x1 = h1;
+            hrow[r] = h;
+            s.x[r] = x;
+            above_x = x;
+            if constexpr (PARTIAL) {
+                if (C == k.outc) s.xs[r] = x;      // E of the matrix's last column has no consumer
+            }
         }
-        if constexpr (LOCAL) s.best = __vimax3_s32(s.best, h0, h1);
-        X[C] = x1;
-        s.x0 = x0;
-        s.x1 = x1;
-        if constexpr (C + 1 < K) Cell2<LOCAL, AFFINE, K, MASK, C + 1>::run(X, F, sc, s, k);
+        if constexpr (LOCAL) {
+            if constexpr (PARTIAL) {
+                if (C < k.nvalid) {
+#pragma unroll
+                    for (int r = 0; r + 1 < R; r += 2) s.best = __vimax3_s32(s.best, hrow[r], hrow[r + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r + 1 < R; r += 2) s.best = __vimax3_s32(s.best, hrow[r], hrow[r + 1]);
+            }
+        }
+        X[C] = above_x;
+        if constexpr (AFFINE) F[C] = above_f;
+        if constexpr (C + 1 < K) CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, C + 1>::run(X, F, sc, s, k);
     }
 };
 
-// shared memory of one warp (sized for R = 2 rows per step, 32 steps per batch)
-struct WarpSmem {
-    int2 in[64];        // left border rows of the current batch (X form, E)
-    int2 out[128];      // right edge rows waiting to be published (ring)
-    uint8_t q[128];     // query symbols (MASK: codes) of the last 128 rows (ring)
+// shared memory of one warp: a batch is always 32 rows (32/R steps)
+struct alignas(16) WarpSmem {
+    int2 in[32];        // left border rows of the current batch (X form, E)
+    int2 out[64];       // right edge rows waiting to be published (ring of two batches)
+    uint8_t q[256];     // query symbols (MASK: codes) of the last 64*R rows (ring)
 };
+
+__device__ __forceinline__ int4 ld_record(const int4* p)
+{
+    int4 v;
+    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_record(int4* p, int4 v)
+{
+    asm volatile("st.volatile.global.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
 
 // One (band, strip) item.  PARTIAL = the strip is cut by the right matrix edge
 // (only the last strip of a job can be): the columns past the edge compute
@@ -318,10 +342,10 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                                              const uint8_t* __restrict__ s_lut /* [2][256] */,
                                              const int lane)
 {
-    static_assert(R == 1 || (R == 2 && !PARTIAL), "two-row tiles are not used for partial strips");
+    static_assert(R == 1 || R == 2 || R == 4, "rows per step");
     constexpr int SW = kWarp * K;
-    constexpr int BR = 32 * R;             // rows per batch
-    constexpr int QM = 64 * R - 1;         // ring masks
+    constexpr int B = 32 / R;              // steps per batch (a batch = 32 rows)
+    constexpr int QM = 64 * R - 1;         // query ring mask
     const int i0 = band * J.band_h;
     const int hb = min(J.band_h, J.h - i0);
     const int j0 = strip * SW;
@@ -337,28 +361,25 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     int* const status = a.status;
     const unsigned long long timeout_ns = a.timeout_ns;
 
-    // left border source (rows of this band)
-    const int* linH;
-    const int* linE;
-    const int* lflag;
-    bool lsys = false;
-    if (strip == 0) {
-        linH = (J.inH ? J.inH : J.colH) + i0;
-        linE = AFFINE ? (J.inH ? J.inE : J.colE) + i0 : nullptr;
-        lflag = J.in_progress;
-        lsys = true;
-    } else {
-        linH = J.colH + i0;
-        linE = AFFINE ? J.colE + i0 : nullptr;
-        lflag = J.progress + (strip - 1);
-    }
-    const bool mirror = last_strip && (J.outH != nullptr);
+    // border records this strip consumes / produces
+    const bool from_inbox = (strip == 0) && (J.in != nullptr);
+    const int4* lin = (from_inbox ? J.in : J.col) + i0;
+    const int expect = from_inbox ? J.in_tag : strip;
+    const int my_tag = strip + 1;
+    int4* const colout = J.col + i0;
+    const bool mirror = last_strip && (J.out != nullptr);
     const uint8_t* qrow = J.q + i0;
 
+#ifdef ANYSEQ_PROFILE
+    const long long pf_item0 = clock64();
+#endif
     // the band above must be complete (its bottom border is our top border)
     if (band > 0) {
         if (!wait_rows(J.progress + strip, i0, false, status, timeout_ns)) return false;
     }
+#ifdef ANYSEQ_PROFILE
+    const long long pf_band = clock64() - pf_item0;
+#endif
 
     int X[K], F[AFFINE ? K : 1], sc[MASK ? 1 : K];
     const int jl = j0 + lane * K;
@@ -407,34 +428,19 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     StepState st;
     st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.mask = 0u; st.qc = 0;
 
+    // rows [base, base+32) of the out lane's edge -> tagged records (coalesced 16-byte stores, no fence)
     auto flush32 = [&](int base) {
-        // rows [base, base+32) of the out lane's edge -> colH/colE (coalesced)
         const int r = base + lane;
         if (r < hb) {
-            const int2 v = sm.out[r & QM];
-            __stcg(J.colH + i0 + r, v.x - go);
-            if constexpr (AFFINE) __stcg(J.colE + i0 + r, v.y);
-            if (mirror) {
-                J.outH[i0 + r] = v.x - go;
-                if constexpr (AFFINE) J.outE[i0 + r] = v.y;
-            }
-        }
-    };
-    auto publish = [&](int rows_abs) {
-        __syncwarp();
-        if (lane == 0) {
-            if (mirror) {
-                __threadfence_system();
-                st_relaxed_sys(J.out_progress, rows_abs);
-            }
-            __threadfence();
-            st_relaxed_gpu(J.progress + strip, rows_abs);
+            const int2 v = sm.out[r & 63];
+            st_record(colout + r, make_int4(v.x - go, my_tag, v.y, my_tag));
+            if (mirror) st_record(J.out + i0 + r, make_int4(v.x - go, J.out_tag, v.y, J.out_tag));
         }
     };
     // MASK: column mask of row i (its query code selects one of the lane's masks)
     auto row_mask = [&](int i) -> unsigned { return s_mask[(int)sm.q[i & QM] * 32 + lane]; };
 
-    // one row of one lane (R = 1 chain): used for R = 1 and for the guarded steps of R = 2
+    // one row of one lane (single chain): used for R = 1 and for the guarded steps of R > 1
     auto relax_row = [&](const int row, const int xl, const int el, const unsigned mask, int& hro, int& ero) {
         if constexpr (MASK) {
             st.mask = mask;
@@ -455,10 +461,10 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #pragma unroll
                 for (int c = 1; c < K; ++c)
                     if (c == k.outc) hs = X[c];
-                sm.out[row & QM] = make_int2(hs, st.es);
+                sm.out[row & 63] = make_int2(hs, st.es);
             }
         } else {
-            if (lane == 31) sm.out[row & QM] = make_int2(hro, ero);
+            if (lane == 31) sm.out[row & 63] = make_int2(hro, ero);
         }
     };
 
@@ -472,12 +478,18 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             el[r] = 0;
             if constexpr (AFFINE) el[r] = __shfl_up_sync(kFull, er[r], 1);
         }
-        if constexpr (R == 1) {
-            const int2 bnd = sm.in[t & 31];
-            if (lane == 0) { xl[0] = bnd.x; el[0] = bnd.y; }
-        } else {
-            const int4 bnd = *reinterpret_cast<const int4*>(&sm.in[2 * (t & 31)]);
-            if (lane == 0) { xl[0] = bnd.x; el[0] = bnd.y; xl[1] = bnd.z; el[1] = bnd.w; }
+        {
+            const int2* bp = &sm.in[R * (t & (B - 1))];
+            if constexpr (R == 1) {
+                const int2 bnd = bp[0];
+                if (lane == 0) { xl[0] = bnd.x; el[0] = bnd.y; }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r += 2) {
+                    const int4 bnd = *reinterpret_cast<const int4*>(bp + r);
+                    if (lane == 0) { xl[r] = bnd.x; el[r] = bnd.y; xl[r + 1] = bnd.z; el[r + 1] = bnd.w; }
+                }
+            }
         }
         const int g = t - lane;                 // row group of this lane
         unsigned mask_next[R];
@@ -486,30 +498,38 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             mask_next[r] = 0u;
             if constexpr (MASK) mask_next[r] = row_mask(R * (g + 1) + r);   // prefetch, off the critical path
         }
-        if constexpr (!GUARD && R == 2) {
-            StepState2 s2;
+        if constexpr (!GUARD && R > 1) {
+            StepStateR<R> s2;
             s2.best = st.best;
-            s2.mask0 = mask_cur[0];
-            s2.mask1 = mask_cur[1];
-            s2.qc0 = 0; s2.qc1 = 0;
-            if constexpr (MASK) {
-                s2.dd0 = diag_plus_sigma_mask<0>(s2.mask0, dcarry, k.one, k.diff_o, k.same_o);
-                s2.dd1 = diag_plus_sigma_mask<0>(s2.mask1, xl[0], k.one, k.diff_o, k.same_o);
-            } else {
-                s2.qc0 = sm.q[(2 * g) & QM];
-                s2.qc1 = sm.q[(2 * g + 1) & QM];
-                s2.dd0 = diag_plus_sigma(s2.qc0, sc[0], dcarry, k.one, k.diff_o, k.same_o);
-                s2.dd1 = diag_plus_sigma(s2.qc1, sc[0], xl[0], k.one, k.diff_o, k.same_o);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                s2.mask[r] = mask_cur[r];
+                s2.qc[r] = 0;
+                const int dg = (r == 0) ? dcarry : xl[r - 1];      // H(row-1, first column - 1)
+                if constexpr (MASK) {
+                    s2.dd[r] = diag_plus_sigma_mask<0>(s2.mask[r], dg, k.one, k.diff_o, k.same_o);
+                } else {
+                    s2.qc[r] = sm.q[(R * g + r) & QM];
+                    s2.dd[r] = diag_plus_sigma(s2.qc[r], sc[0], dg, k.one, k.diff_o, k.same_o);
+                }
+                s2.x[r] = xl[r];
+                s2.e[r] = el[r];
             }
             dcarry = xl[R - 1];
-            s2.x0 = xl[0]; s2.e0 = el[0];
-            s2.x1 = xl[R - 1]; s2.e1 = el[R - 1];
-            Cell2<LOCAL, AFFINE, K, MASK, 0>::run(X, F, sc, s2, k);
-            hr[0] = s2.x0; er[0] = s2.e0;
-            hr[R - 1] = s2.x1; er[R - 1] = s2.e1;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { s2.xs[r] = 0; s2.es[r] = 0; }
+            CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, 0>::run(X, F, sc, s2, k);
+#pragma unroll
+            for (int r = 0; r < R; ++r) { hr[r] = s2.x[r]; er[r] = s2.e[r]; }
             st.best = s2.best;
-            if (lane == 31)
-                *reinterpret_cast<int4*>(&sm.out[(2 * g) & QM]) = make_int4(s2.x0, s2.e0, s2.x1, s2.e1);
+            if (lane == outlane) {
+#pragma unroll
+                for (int r = 0; r < R; r += 2) {
+                    const int4 v = PARTIAL ? make_int4(s2.xs[r], s2.es[r], s2.xs[r + 1], s2.es[r + 1])
+                                           : make_int4(hr[r], er[r], hr[r + 1], er[r + 1]);
+                    *reinterpret_cast<int4*>(&sm.out[(R * g + r) & 63]) = v;
+                }
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -531,58 +551,76 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #define PF_BEGIN()
 #define PF_END(acc)
 #endif
-    for (int tb = 0; tb < T; tb += 32) {
+    // speculative prefetch of the first batch of border records and query symbols
+    int4 rec = make_int4(0, expect, kNegInf, expect);
+    uint8_t qsym = 0;
+    if (lane < hb) {
+        rec = ld_record(lin + lane);
+        qsym = qrow[lane];
+    }
+    for (int tb = 0; tb < T; tb += B) {
         __syncwarp();
         PF_BEGIN();
+        const int rb = R * tb;                  // first row of the batch
         // (1) publish the edge rows the out lane finished so far
         {
             const int completed = min(max(R * (tb - outlane), 0), hb);
-            bool any = false;
             while (completed - flushed >= 32) {
                 flush32(flushed);
                 flushed += 32;
-                any = true;
             }
-            if (any && flushed < hb) publish(i0 + flushed);   // the final publish is below
         }
-        // (2) fetch the next batch of rows of the left border and of the query
-        {
-            const int rb = R * tb;              // first row of the batch
-            PF_END(pf_io);
+        PF_END(pf_io);
+        // (2) the batch's border records were prefetched a batch ago; a record is
+        //     valid when both of its tags are the expected one
+        if (rb < hb) {
             PF_BEGIN();
-            if (rb < hb && lflag != nullptr) {
-                if (!wait_rows(lflag, i0 + min(rb + BR, hb), lsys, status, timeout_ns)) return false;
+            const int r = rb + lane;
+            bool ok = (r >= hb) || (rec.y == expect && (!AFFINE || rec.w == expect));
+            if (!__all_sync(kFull, ok)) {
+                const unsigned long long t0 = global_timer_ns();
+                unsigned spins = 0;
+                while (true) {
+                    if (r < hb) rec = ld_record(lin + r);
+                    ok = (r >= hb) || (rec.y == expect && (!AFFINE || rec.w == expect));
+                    if (__all_sync(kFull, ok)) break;
+                    if ((++spins & 63u) == 0u) {
+                        bool fail = *(volatile int*)status != kStatusOk;
+                        if (!fail && global_timer_ns() - t0 > timeout_ns) {
+                            if (atomicCAS(status, kStatusOk, kStatusTimeout) == kStatusOk) {
+                                status[1] = expect; status[2] = rec.y; status[3] = strip;
+                            }
+                            fail = true;
+                        }
+                        if (__any_sync(kFull, fail)) return false;
+                    }
+                }
             }
             PF_END(pf_wait);
             PF_BEGIN();
-#pragma unroll
-            for (int u = 0; u < R; ++u) {
-                const int r = rb + 32 * u + lane;
-                int2 v = make_int2(0, kNegInf);
-                uint8_t qv = 0;
-                if (r < hb) {
-                    v.x = __ldcg(linH + r) + go;
-                    if constexpr (AFFINE) v.y = __ldcg(linE + r);
-                    qv = MASK ? s_lut[qrow[r]] : qrow[r];
-                }
-                sm.in[32 * u + lane] = v;
-                sm.q[r & QM] = qv;
+            sm.in[lane] = make_int2(rec.x + go, rec.z);
+            sm.q[r & QM] = MASK ? s_lut[qsym] : qsym;
+            // prefetch the next batch (its records may not be there yet: checked next time)
+            const int rn = r + 32;
+            if (rn < hb) {
+                rec = ld_record(lin + rn);
+                qsym = qrow[rn];
             }
             __syncwarp();
             if constexpr (MASK) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) mask_cur[r] = row_mask(R * (tb - lane) + r);   // rows of this lane at step tb
+                for (int r2 = 0; r2 < R; ++r2) mask_cur[r2] = row_mask(R * (tb - lane) + r2);   // rows of this lane at step tb
             }
+            PF_END(pf_io);
         }
-        PF_END(pf_io);
         PF_BEGIN();
-        // (3) 32 anti-diagonal steps; batches in which every row of every lane is
+        // (3) B anti-diagonal steps; batches in which every row of every lane is
         //     inside the band run the unguarded body
-        if (tb >= 31 && R * (tb + 32) <= hb) {
+        if (tb >= 31 && R * (tb + B) <= hb) {
 #pragma unroll 1
-            for (int t = tb; t < tb + 32; ++t) step(std::false_type{}, t);
+            for (int t = tb; t < tb + B; ++t) step(std::false_type{}, t);
         } else {
-            const int tend = min(tb + 32, T);
+            const int tend = min(tb + B, T);
 #pragma unroll 1
             for (int t = tb; t < tend; ++t) step(std::true_type{}, t);
         }
@@ -594,7 +632,10 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         atomicAdd(pc + 0, (unsigned long long)pf_wait);
         atomicAdd(pc + 1, (unsigned long long)pf_io);
         atomicAdd(pc + 2, (unsigned long long)pf_steps);
-        atomicAdd(pc + 3, (unsigned long long)((T + 31) / 32));
+        atomicAdd(pc + 3, (unsigned long long)((T + B - 1) / B));
+        atomicAdd(pc + 4, (unsigned long long)pf_band);
+        atomicAdd(pc + 5, (unsigned long long)(clock64() - pf_item0));
+        atomicAdd(pc + 6, 1ull);
     }
 #endif
 
@@ -619,29 +660,39 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
         if (lane == 0) atomicMax(J.best, best);
     }
-    publish(i0 + hb);
+    // band hand-over: bottom border + corner are visible before the row counter
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        st_relaxed_gpu(J.progress + strip, i0 + hb);
+    }
     return true;
 }
 
-// CTAs per SM the register allocation is capped for: the recurrence has a 3-deep
-// dependent chain per cell and needs >= 4 warps per scheduler to hide it.
-template <int K, bool MASK>
-constexpr int strip_min_blocks()
-{
-#ifndef ANYSEQ_K32_MASK_BLOCKS
-#define ANYSEQ_K32_MASK_BLOCKS 4
+// rows per lane and step of each kernel variant
+#ifndef ANYSEQ_ROWS_K32
+#define ANYSEQ_ROWS_K32 2
 #endif
-    return K >= 32 ? (MASK ? ANYSEQ_K32_MASK_BLOCKS : 4) : (K >= 16 ? 5 : 6);
-}
-
-// rows per lane and step: two-row tiles for the wide MASK kernels
-#ifndef ANYSEQ_ROWS_WIDE
-#define ANYSEQ_ROWS_WIDE 2
+#ifndef ANYSEQ_ROWS_K16
+#define ANYSEQ_ROWS_K16 2
 #endif
 template <int K, bool MASK>
 struct StripRows {
-    static constexpr int value = (MASK && K >= 16) ? ANYSEQ_ROWS_WIDE : 1;
+    static constexpr int value = !MASK ? 1 : (K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1));
 };
+
+// CTAs per SM the register allocation is capped for.  Single-row kernels need
+// >= 4 warps per scheduler to hide the 3-deep dependent chain per cell; multi-row
+// tiles carry R chains per warp and run with 1-3 CTAs per SM (engine.cu), so
+// they may use more registers.
+template <int K, bool MASK>
+constexpr int strip_min_blocks()
+{
+    constexpr int R = StripRows<K, MASK>::value;
+    if (R >= 4) return 1;
+    if (R == 2) return K >= 32 ? 2 : 3;
+    return K >= 32 ? 4 : (K >= 16 ? 5 : 6);
+}
 
 template <bool LOCAL, bool AFFINE, int K, bool MASK>
 __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_kernel(const KernelArgs a)
@@ -664,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
     unsigned* s_mask = s_dyn + warp * a.ncodes * 32;
     // the query ring is read one row ahead (mask prefetch): never let an
     // uninitialised byte be used as a code
-    for (int x = lane; x < 128; x += 32) s_warp[warp].q[x] = 0;
+    for (int x = lane; x < 256; x += 32) s_warp[warp].q[x] = 0;
     __syncwarp();
 
     // Items are claimed in index order from a global counter (the first round is
@@ -681,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)
-            ok = process_item<LOCAL, AFFINE, K, true, MASK, 1>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, true, MASK, R>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         else
             ok = process_item<LOCAL, AFFINE, K, false, MASK, R>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         if (!ok) return;

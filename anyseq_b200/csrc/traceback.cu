@@ -43,16 +43,17 @@ struct HbPart {          // one part of a Hirschberg level
 
 // hb_sum: argmax over split rows of L(i) + R(len-i-2) with the two border
 // candidates, in the reference's candidate order.  One CTA per part.
-__global__ void hb_sum_kernel(const HbPart* __restrict__ parts, int nparts, const int* __restrict__ colL,
-                              const int* __restrict__ colR, int* __restrict__ splits /* index 0 = slot -1 */,
+__global__ void hb_sum_kernel(const HbPart* __restrict__ parts, int nparts, const int4* __restrict__ colL,
+                              const int4* __restrict__ colR, int* __restrict__ splits /* index 0 = slot -1 */,
                               int half, int bpp2, int init_global, int gap)
 {
     __shared__ unsigned long long s_key[32];
     __shared__ int s_idx[32];
     for (int p = blockIdx.x; p < nparts; p += gridDim.x) {
         const HbPart P = parts[p];
-        const int* L = colL + P.off;
-        const int* R = colR + P.off;
+        // last-column scores of the two halves: .x of the border records
+        auto L = [&](int i) -> int { return __ldcg(reinterpret_cast<const int*>(colL + P.off + i)); };
+        auto R = [&](int i) -> int { return __ldcg(reinterpret_cast<const int*>(colR + P.off + i)); };
         const int len = P.len;
         // key = (value, -priority): larger wins; priority = position in the reference's scan
         unsigned long long best = 0ull;   // below every real candidate
@@ -66,11 +67,11 @@ __global__ void hb_sum_kernel(const HbPart* __restrict__ parts, int nparts, cons
         if (len > 0 && threadIdx.x == 0) {
             const int init_l = init_global ? half * gap : 0;             // init_scores(lhw - 1)
             const int init_r = init_global ? P.rhw * gap : 0;            // init_scores(rhw - 1)
-            consider(init_l + R[len - 1], 0u, -1);
-            consider(L[len - 1] + init_r, 1u, len - 1);
+            consider(init_l + R(len - 1), 0u, -1);
+            consider(L(len - 1) + init_r, 1u, len - 1);
         }
         for (int i = threadIdx.x; i < len - 1; i += blockDim.x) {
-            const int val = L[i] + R[len - i - 2];
+            const int val = L(i) + R(len - i - 2);
             const unsigned prio = (unsigned)(i % bpp2) * per_block + (unsigned)(i / bpp2) + 2u;
             consider(val, prio, i);
         }
@@ -272,7 +273,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
     };
 
     const size_t rowlen = (size_t)std::max(part_width, kMinPartW) + 1024;
-    if (colH_.ensure(sizeof(int) * (size_t)m) || colH2_.ensure(sizeof(int) * (size_t)m) ||
+    if (col_.ensure(sizeof(int4) * (size_t)m) || col2_.ensure(sizeof(int4) * (size_t)m) ||
         rowH_.ensure(sizeof(int) * rowlen) || aux_.ensure(sizeof(int) * ((size_t)nb + 1)))
         return ANYSEQ_ERR_NO_DEVICE;
     int* d_splits = aux_.as<int>();
@@ -319,7 +320,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
                 J.nstrips = (w + SW - 1) / SW;
                 J.band_h = pick_band(len, J.nstrips, resident, K);
                 J.nbands = (len + J.band_h - 1) / J.band_h;
-                J.colH = (side == 0 ? colH_.as<int>() : colH2_.as<int>()) + off;
+                J.col = (side == 0 ? col_.as<int4>() : col2_.as<int4>()) + off;
                 J.rowH = rowH_.as<int>() + c0;
                 J.corner = nullptr;   // patched below (offset into corner_/progress_)
                 J.item_begin = strip_total;
@@ -343,8 +344,8 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         if (aux2_.ensure(sizeof(HbPart) * (size_t)std::max(nparts, 1))) return ANYSEQ_ERR_NO_DEVICE;
         ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(aux2_.ptr, parts.data(), sizeof(HbPart) * (size_t)nparts, cudaMemcpyHostToDevice, stream_));
         const int bpp2 = part_width / std::min(kRefBlockW, part_width);
-        hb_sum_kernel<<<std::min(nparts, 4096), 256, 0, stream_>>>(aux2_.as<HbPart>(), nparts, colH_.as<int>(),
-                                                                   colH2_.as<int>(), d_splits, half, bpp2,
+        hb_sum_kernel<<<std::min(nparts, 4096), 256, 0, stream_>>>(aux2_.as<HbPart>(), nparts, col_.as<int4>(),
+                                                                   col2_.as<int4>(), d_splits, half, bpp2,
                                                                    init_global, sp.gap_extend);
         ANYSEQ_CUDA_CHECK(cudaGetLastError());
         launches += 1;

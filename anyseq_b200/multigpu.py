@@ -43,9 +43,13 @@ class StripWavefront:
                 aligner._check(self._lib.anyseq_strip_inbox_open(aligner.handle, buf, rows, C.byref(self.next_inbox)))
 
     def reset(self):
-        """zero this rank's inbox counter; every rank must call it (ends with a barrier)"""
+        """re-synchronise the run counters of both ends of every inbox and clear the owned
+        one; every rank must call it (ends with a barrier).  Not needed between runs: border
+        records carry a per-run tag."""
         if self.inbox:
             self.al._check(self._lib.anyseq_strip_inbox_reset(self.al.handle, self.inbox))
+        if self.next_inbox:
+            self.al._check(self._lib.anyseq_strip_inbox_reset(self.al.handle, self.next_inbox))
         if self.world > 1:
             self.dist.barrier()
 

@@ -192,9 +192,12 @@ def main():
     wave = StripWavefront(al, rank, world, m, dist)
     torch.cuda.synchronize()
 
+    wave.reset()
+
     def step_resident():
         flush.zero_()
-        wave.reset()
+        if dist is not None:
+            dist.barrier()          # every rank has finished the previous run (inbox rows may be rewritten)
         torch.cuda.synchronize()
         part = wave.run(MODE, scoring, d_q.data_ptr(), m, d_s.data_ptr(), c0, c1, n)
         return part
@@ -236,7 +239,8 @@ def main():
                 # the reference-facing C ABI call with HOST pointers: H2D of both
                 # sequences, kernels, D2H of the result, all inside the call
                 return al.score(MODE, h_q.numpy(), h_s.numpy(), scoring).score
-            wave.reset()
+            if dist is not None:
+                dist.barrier()
             dq = h_q.cuda(non_blocking=True)
             ds = h_s.cuda(non_blocking=True)
             torch.cuda.synchronize()
