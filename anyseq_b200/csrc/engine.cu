@@ -139,8 +139,7 @@ static int default_blocks_per_sm(int K, bool mask, int occupancy_max)
 {
     int nb = occupancy_max;
     const int R = rows_per_step(K, mask);
-    if (R >= 4) nb = std::min(nb, 1);
-    else if (R == 2) nb = std::min(nb, K >= 32 ? 2 : 3);
+    if (R >= 2) nb = std::min(nb, 2);
     return nb;
 }
 
@@ -279,25 +278,20 @@ int Engine::pick_K(int n) const
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
-    // Throughput model in cells per clock per GPU, constants measured on B200
-    // (profiles/): at most one warp works on a strip at a time, so
-    // min(nstrips, resident warps) warps are busy, each at its lone-warp rate,
-    // up to the rate the whole chip sustains with that kernel variant.
-    struct Variant { int K; double lone; double chip; int blocks; };
-    static const Variant mask_variants[] = {{32, 2.8, 1750.0, 2}, {16, 2.4, 1500.0, 3}, {8, 1.3, 1000.0, 6}, {4, 1.0, 600.0, 6}};
-    static const Variant byte_variants[] = {{16, 1.4, 1300.0, 5}, {8, 1.2, 900.0, 6}, {4, 0.9, 550.0, 6}};
-    const Variant* v = use_mask_ ? mask_variants : byte_variants;
-    const int nv = use_mask_ ? 4 : 3;
-    double best = -1.0;
-    int bestK = 4;
-    for (int i = 0; i < nv; ++i) {
-        const double scale = sm_count / 148.0;
-        const double resident = sm_count * 4.0 * v[i].blocks;
-        const double nstrips = (n + 32.0 * v[i].K - 1) / (32.0 * v[i].K);
-        const double rate = std::min(v[i].chip * scale, std::min(nstrips, resident) * v[i].lone);
-        if (rate > best * 1.02) { best = rate; bestK = v[i].K; }
+    // At most one warp works on a strip at a time, so the strips must at least
+    // cover the warps the kernel variant runs with (2 CTAs/SM = 1184 warps for the
+    // two-row tile kernels, 3552 for the narrow single-row ones); beyond that,
+    // wider strips have less per-step overhead.  Thresholds from B200
+    // measurements (profiles/): n = 575 k runs 2.8 TCUPS at K=16, 2.4 at K=32.
+    if (use_mask_) {
+        if (n >= 1100000) return 32;
+        if (n >= 280000) return 16;
+        if (n >= 70000) return 8;
+        return 4;
     }
-    return bestK;
+    if (n >= 1500000) return 16;      // generic kernels keep subject bytes in registers: K <= 16
+    if (n >= 200000) return 8;
+    return 4;
 }
 
 // Band height.  Items are taken in index order by a window of `resident` warps,
