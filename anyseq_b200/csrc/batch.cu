@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
             const int outlane = (n - 1) / K, outc = (n - 1) % K;
             int hr = 0, er = 0;
             int colbest = kScoreMin;     // semiglobal: max over H(i, n-1), kept by lane `outlane`
-            StepState st;
-            st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.mask = 0u; st.qc = 0;
+            StepState<1> st;
+            st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.tm[0] = 0u; st.qc = 0;
             auto row_mask = [&](int i) -> unsigned { return s_mask[(int)rq[i & 63] * 32 + lane]; };
             const int T = m + outlane;
             for (int tb = 0; tb < T; tb += 32) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                     if (r < m) v = MASK ? s_lut[rows[r]] : rows[r];
                     rq[r & 63] = v;
                     __syncwarp();
-                    if constexpr (MASK) st.mask = row_mask(tb - lane);
+                    if constexpr (MASK) st.tm[0] = row_mask(tb - lane);
                 }
                 const int tend = min(tb + 32, T);
 #pragma unroll 1
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                     if constexpr (MASK) mask_next = row_mask(i + 1);
                     if ((unsigned)i < (unsigned)m) {
                         if constexpr (MASK) {
-                            st.dd = diag_plus_sigma_mask<0>(st.mask, dcarry, k.one, k.diff_o, k.same_o);
+                            st.dd = diag_plus_sigma_mask<0>(st.tm[0], dcarry, k.one, k.diff_o, k.same_o);
                         } else {
                             st.qc = rq[i & 63];
                             st.dd = diag_plus_sigma(st.qc, sc[0], dcarry, k.one, k.diff_o, k.same_o);
@@ -176,14 +176,14 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                         dcarry = xl;
                         st.xleft = xl;
                         st.e = el;
-                        Cell<LOCAL, AFFINE, K, false, MASK, 0>::run(X, F, sc, st, k);
+                        Cell<LOCAL, AFFINE, K, false, MASK, 1, 0, 0>::run(X, F, sc, st, k);
                         hr = st.xleft;
                         er = st.e;
                         if constexpr (MODE == kSemiglobal) {
                             if (lane == outlane) colbest = max(colbest, pick_column<K>(X, outc));
                         }
                     }
-                    if constexpr (MASK) st.mask = mask_next;
+                    if constexpr (MASK) st.tm[0] = mask_next;
                 }
             }
             // result extraction: src/scoring.impala:29-137 (values only)

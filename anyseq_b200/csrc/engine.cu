@@ -131,21 +131,28 @@ static int rows_per_step(int K, bool mask)
     return K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1);
 }
 
-// CTAs per SM actually launched.  Two-row tiles carry two dependent chains per
-// warp, so two warps per scheduler already saturate the issue slots, and fewer
-// warps per scheduler means less spread in per-warp progress -- which is what
-// the strip-to-strip pipeline is sensitive to (measured: profiles/).
-static int default_blocks_per_sm(int K, bool mask, int occupancy_max)
+// CTAs per SM actually launched.  Multi-row tiles carry R dependent chains per
+// warp, so 2-3 warps per scheduler saturate the issue slots; and never more warps
+// than strips: at most one warp works on a strip at a time, the others would only
+// poll and add spread to the progress of the busy ones -- which is what the
+// strip-to-strip pipeline is sensitive to (measured: profiles/).
+static int default_blocks_per_sm(int K, bool mask, int occupancy_max, long long nstrips, int sm_count)
 {
     int nb = occupancy_max;
-    const int R = rows_per_step(K, mask);
-    if (R >= 2) nb = std::min(nb, 2);
+    if (rows_per_step(K, mask) >= 2) {
+        const long long per_round = 4LL * sm_count;              // warps of one CTA per SM
+        const int want = (int)std::max<long long>(1, (nstrips + per_round / 2) / per_round);
+        nb = std::min(nb, std::min(3, want));
+    }
     return nb;
 }
 
-static size_t mask_smem_bytes(bool mask, int ncodes)
+// dynamic shared memory of the MASK kernels: [warps][ncodes][32 lanes][W words] spread column masks
+static size_t mask_smem_bytes(bool mask, int ncodes, int K)
 {
-    return mask ? sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock : 0;
+    if (!mask) return 0;
+    const int words = std::max(1, rows_per_step(K, mask) * K / 32);
+    return sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock * words;
 }
 
 // ---------------------------------------------------------------------------
@@ -240,14 +247,14 @@ void Engine::destroy()
     h_misc_ = nullptr; ev0_ = ev1_ = nullptr; stream_ = nullptr;
 }
 
-int Engine::resident_warps(int K, bool local, bool affine)
+int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
     KernelFn fn = pick_kernel(local, affine, K, use_mask_);
     if (!fn) return 0;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, ncodes_)) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, ncodes_, K)) != cudaSuccess) return 0;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, nb);
+    else nb = default_blocks_per_sm(K, use_mask_, nb, nstrips, sm_count);
     return nb * kWarpsPerBlock * sm_count;
 }
 
@@ -282,9 +289,10 @@ int Engine::pick_K(int n) const
     // cover the warps the kernel variant runs with (2 CTAs/SM = 1184 warps for the
     // two-row tile kernels, 3552 for the narrow single-row ones); beyond that,
     // wider strips have less per-step overhead.  Thresholds from B200
-    // measurements (profiles/): n = 575 k runs 2.8 TCUPS at K=16, 2.4 at K=32.
+    // measurements (profiles/): n = 575 k runs 2.8 TCUPS at K=16 and 1.7 at K=32, n = 1.15 M
+    // 3.3 at K=16 and 3.1 at K=32, n = 2.3 M 3.6 at K=32.
     if (use_mask_) {
-        if (n >= 1100000) return 32;
+        if (n >= 1800000) return 32;
         if (n >= 280000) return 16;
         if (n >= 70000) return 8;
         return 4;
@@ -334,12 +342,14 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
 
     KernelFn fn = pick_kernel(local, affine, K, use_mask_);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
-    const size_t dyn_smem = mask_smem_bytes(use_mask_, ncodes_);
+    const size_t dyn_smem = mask_smem_bytes(use_mask_, ncodes_, K);
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
+    long long strips_total = 0;
+    for (const Job& j : jobs) strips_total += j.nstrips;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, nb);
+    else nb = default_blocks_per_sm(K, use_mask_, nb, strips_total, sm_count);
     long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
 
@@ -438,7 +448,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int K = pick_K(w);
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
-    const int resident = resident_warps(K, local, affine);
+    const int resident = resident_warps(K, local, affine, nstrips);
     const int band_h = pick_band(m, nstrips, resident, K);
 
     const size_t wpad = (size_t)nstrips * SW;

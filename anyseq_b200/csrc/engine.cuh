@@ -93,7 +93,7 @@ public:
     int device = -1;
     int sm_count = 0;
     char name[64] = {0};
-    int resident_warps(int K, bool local, bool affine);
+    int resident_warps(int K, bool local, bool affine, long long nstrips = 1LL << 40);
 
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,

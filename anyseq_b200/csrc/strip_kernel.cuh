@@ -124,6 +124,11 @@ __device__ __forceinline__ int ld_relaxed_sys(const int* p)
     return v;
 }
 
+struct StepConst;
+// bit (BASE + r) of a tile mask, r in 0..3 known after unrolling
+template <int BASE, int W>
+__device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int d, const StepConst& k);
+
 // Wait until *flag >= need.  Executed by all lanes of a warp (same address:
 // one transaction).  Fast path: one acquire load.  Slow path: relaxed polls (an
 // acquire load costs a CCTL.IVALL -- a whole-L1 invalidate -- per poll), then one
@@ -173,7 +178,18 @@ __device__ __forceinline__ void load_row_ints(const int* __restrict__ p, int (&d
     }
 }
 
-// state of one lane during one anti-diagonal step
+// Tile mask (MASK kernels): bit (c*R + r) of the W-word mask says "subject column c
+// equals the query symbol of row r of the lane's current R-row group"; it is the
+// sum over r of (spread column mask of row r's code) << r.  Consecutive cells of
+// the 2-D wavefront read consecutive bits, which ptxas turns into R2P (seven
+// predicates per instruction) instead of one LOP3 per cell.
+template <int R, int K>
+struct TileWords {
+    static constexpr int value = (R * K + 31) / 32;
+};
+
+// state of one lane during one single-row chain
+template <int W>
 struct StepState {
     int dd;          // H(i-1, j-1) + sigma of the cell about to be relaxed
     int e;           // E of the cell to the left
@@ -181,7 +197,7 @@ struct StepState {
     int best;        // LOCAL: running maximum
     int hprev;       // LOCAL: H of the previous (even) column, folded pairwise with VIMNMX3
     int es;          // PARTIAL: E of the edge column
-    unsigned mask;   // MASK: columns whose subject symbol equals the row's query symbol
+    unsigned tm[W];  // MASK: tile mask of the lane's current row group
     int qc;          // !MASK: the row's query byte
 };
 
@@ -190,22 +206,36 @@ struct StepConst {
     int nvalid, outc;   // PARTIAL only
 };
 
+template <int BASE, int W>
+__device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int d, const StepConst& k)
+{
+    // r is a compile-time constant after unrolling; the switch folds away
+    switch (r) {
+        case 0: return diag_plus_sigma_mask<(BASE + 0) % 32>(tm[(BASE + 0) / 32 < W ? (BASE + 0) / 32 : 0], d, k.one, k.diff_o, k.same_o);
+        case 1: return diag_plus_sigma_mask<(BASE + 1) % 32>(tm[(BASE + 1) / 32 < W ? (BASE + 1) / 32 : 0], d, k.one, k.diff_o, k.same_o);
+        case 2: return diag_plus_sigma_mask<(BASE + 2) % 32>(tm[(BASE + 2) / 32 < W ? (BASE + 2) / 32 : 0], d, k.one, k.diff_o, k.same_o);
+        default: return diag_plus_sigma_mask<(BASE + 3) % 32>(tm[(BASE + 3) / 32 < W ? (BASE + 3) / 32 : 0], d, k.one, k.diff_o, k.same_o);
+    }
+}
+
 // Cell C of the lane's K columns, then cell C+1, ... (compile-time recursion so
 // that the mask bit is an immediate).  Per cell (SASS, cuobjdump):
 //   Gotoh : VIADDMNMX (E), VIADDMNMX (F), VIMNMX3[.RELU] + 1/7 R2P | IMAD, @p IMAD, IMAD
 //   linear: VIMNMX, VIADDMNMX[.RELU]               + 1/7 R2P | IMAD, @p IMAD
 // The diagonal term of cell C+1 is formed before X[C] is overwritten, so the
 // old value dies in place and no register moves are needed.
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int C>
+// RS / RO: the row is row RO of an RS-row group (selects its bits in the tile mask).
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C>
 struct Cell {
-    template <int KF, int KS>
-    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState& s,
+    template <int KF, int KS, int W>
+    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState<W>& s,
                                                const StepConst& k)
     {
         const int up = X[C];
         const int dd = s.dd;
         if constexpr (C + 1 < K) {
-            if constexpr (MASK) s.dd = diag_plus_sigma_mask<C + 1>(s.mask, up, k.one, k.diff_o, k.same_o);
+            constexpr int BIT = (C + 1) * RS + RO;
+            if constexpr (MASK) s.dd = diag_plus_sigma_mask<BIT % 32>(s.tm[BIT / 32], up, k.one, k.diff_o, k.same_o);
             else s.dd = diag_plus_sigma(s.qc, sc[C + 1], up, k.one, k.diff_o, k.same_o);
         }
         int h;
@@ -233,7 +263,7 @@ struct Cell {
         const int x = AFFINE ? imad_add(h, k.one, k.go) : h;
         X[C] = x;
         s.xleft = x;
-        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, C + 1>::run(X, F, sc, s, k);
+        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1>::run(X, F, sc, s, k);
     }
 };
 
@@ -243,12 +273,12 @@ struct Cell {
 // small 2-D wavefront instead of one chain: R times the instruction-level
 // parallelism, 1/R of the per-cell step overhead, and one such warp per
 // scheduler is enough to keep the issue slots busy.
-template <int R>
+template <int R, int W>
 struct StepStateR {
     int dd[R];           // diag + sigma of the R cells about to be relaxed
     int e[R];            // E to the left, per row
     int x[R];            // X to the left, per row
-    unsigned mask[R];    // MASK: column masks of the R rows
+    unsigned tm[W];      // MASK: tile mask of the group
     int qc[R];           // !MASK: query bytes of the R rows
     int best;            // LOCAL
     int xs[R], es[R];    // PARTIAL: X and E of the edge column, per row
@@ -256,8 +286,8 @@ struct StepStateR {
 
 template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, int C>
 struct CellR {
-    template <int KF, int KS>
-    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepStateR<R>& s,
+    template <int KF, int KS, int W>
+    static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepStateR<R, W>& s,
                                                const StepConst& k)
     {
         int above_x = X[C];                      // X of the cell above (row -1 of this group: the stored row)
@@ -269,7 +299,7 @@ struct CellR {
             const int dd = s.dd[r];
             if constexpr (C + 1 < K) {
                 // diagonal term of cell (r, C+1): H(r-1, C) = the cell above this one
-                if constexpr (MASK) s.dd[r] = diag_plus_sigma_mask<C + 1>(s.mask[r], above_x, k.one, k.diff_o, k.same_o);
+                if constexpr (MASK) s.dd[r] = diag_mask_bit<(C + 1) * R>(s.tm, r, above_x, k);
                 else s.dd[r] = diag_plus_sigma(s.qc[r], sc[C + 1], above_x, k.one, k.diff_o, k.same_o);
             }
             int h, x;
@@ -338,7 +368,7 @@ __device__ __forceinline__ void st_record(int4* p, int4 v)
 template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
                                              const KernelArgs& a, WarpSmem& sm,
-                                             unsigned* __restrict__ s_mask /* [ncodes][32] */,
+                                             unsigned* __restrict__ s_mask /* [ncodes][32][W] spread column masks */,
                                              const uint8_t* __restrict__ s_lut /* [2][256] */,
                                              const int lane)
 {
@@ -346,6 +376,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     constexpr int SW = kWarp * K;
     constexpr int B = 32 / R;              // steps per batch (a batch = 32 rows)
     constexpr int QM = 64 * R - 1;         // query ring mask
+    constexpr int W = TileWords<R, K>::value;
     const int i0 = band * J.band_h;
     const int hb = min(J.band_h, J.h - i0);
     const int j0 = strip * SW;
@@ -392,15 +423,18 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         F[0] = 0;
     }
     if constexpr (MASK) {
-        // per-lane column masks, one per alphabet code; code 0 matches nothing
+        // per-lane column masks, one per alphabet code, spread by R (column c -> bit c*R);
+        // code 0 matches nothing
         sc[0] = 0;
         __syncwarp();
-        for (int cd = 0; cd < a.ncodes; ++cd) s_mask[cd * 32 + lane] = 0u;
+        for (int cd = 0; cd < a.ncodes; ++cd)
+#pragma unroll
+            for (int w = 0; w < W; ++w) s_mask[(cd * 32 + lane) * W + w] = 0u;
 #pragma unroll 4
         for (int c = 0; c < K; ++c) {
             const int j = jl + c;
             const int cd = (j < J.w) ? (int)s_lut[256 + J.s[j]] : 0;
-            if (cd) s_mask[cd * 32 + lane] |= 1u << c;
+            if (cd) s_mask[(cd * 32 + lane) * W + (c * R) / 32] |= 1u << ((c * R) % 32);
         }
         __syncwarp();
     } else {
@@ -421,12 +455,16 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     const int ngroups = (hb + R - 1) / R;  // row groups of R rows
     const int T = ngroups + outlane;       // number of steps
     int hr[R], er[R];
-    unsigned mask_cur[R];
+    unsigned tm_cur[W];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { hr[r] = 0; er[r] = 0; mask_cur[r] = 0u; }
+    for (int r = 0; r < R; ++r) { hr[r] = 0; er[r] = 0; }
+#pragma unroll
+    for (int w = 0; w < W; ++w) tm_cur[w] = 0u;
     int flushed = 0;                       // rows published so far
-    StepState st;
-    st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.mask = 0u; st.qc = 0;
+    StepState<W> st;
+    st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.qc = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) st.tm[w] = 0u;
 
     // rows [base, base+32) of the out lane's edge -> tagged records (coalesced 16-byte stores, no fence)
     auto flush32 = [&](int base) {
@@ -437,14 +475,25 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             if (mirror) st_record(J.out + i0 + r, make_int4(v.x - go, J.out_tag, v.y, J.out_tag));
         }
     };
-    // MASK: column mask of row i (its query code selects one of the lane's masks)
-    auto row_mask = [&](int i) -> unsigned { return s_mask[(int)sm.q[i & QM] * 32 + lane]; };
+    // MASK: tile mask of row group g = sum over its rows of (spread mask of the row's code) << r
+    auto tile_mask = [&](int g, unsigned (&tm)[W]) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) tm[w] = 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned* mp = s_mask + ((int)sm.q[(R * g + r) & QM] * 32 + lane) * W;
+#pragma unroll
+            for (int w = 0; w < W; ++w) tm[w] += mp[w] << r;
+        }
+    };
 
     // one row of one lane (single chain): used for R = 1 and for the guarded steps of R > 1
-    auto relax_row = [&](const int row, const int xl, const int el, const unsigned mask, int& hro, int& ero) {
+    auto relax_row = [&](auto ro_tag, const int row, const int xl, const int el, int& hro, int& ero) {
+        constexpr int RO = decltype(ro_tag)::value;
         if constexpr (MASK) {
-            st.mask = mask;
-            st.dd = diag_plus_sigma_mask<0>(mask, dcarry, k.one, k.diff_o, k.same_o);
+#pragma unroll
+            for (int w = 0; w < W; ++w) st.tm[w] = tm_cur[w];
+            st.dd = diag_plus_sigma_mask<RO>(st.tm[0], dcarry, k.one, k.diff_o, k.same_o);
         } else {
             st.qc = sm.q[row & QM];
             st.dd = diag_plus_sigma(st.qc, sc[0], dcarry, k.one, k.diff_o, k.same_o);
@@ -452,7 +501,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         dcarry = xl;
         st.xleft = xl;
         st.e = el;
-        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, 0>::run(X, F, sc, st, k);
+        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0>::run(X, F, sc, st, k);
         hro = st.xleft;
         ero = st.e;
         if constexpr (PARTIAL) {
@@ -492,22 +541,21 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             }
         }
         const int g = t - lane;                 // row group of this lane
-        unsigned mask_next[R];
+        unsigned tm_next[W];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            mask_next[r] = 0u;
-            if constexpr (MASK) mask_next[r] = row_mask(R * (g + 1) + r);   // prefetch, off the critical path
-        }
+        for (int w = 0; w < W; ++w) tm_next[w] = 0u;
+        if constexpr (MASK) tile_mask(g + 1, tm_next);            // prefetch, off the critical path
         if constexpr (!GUARD && R > 1) {
-            StepStateR<R> s2;
+            StepStateR<R, W> s2;
             s2.best = st.best;
 #pragma unroll
+            for (int w = 0; w < W; ++w) s2.tm[w] = tm_cur[w];
+#pragma unroll
             for (int r = 0; r < R; ++r) {
-                s2.mask[r] = mask_cur[r];
                 s2.qc[r] = 0;
                 const int dg = (r == 0) ? dcarry : xl[r - 1];      // H(row-1, first column - 1)
                 if constexpr (MASK) {
-                    s2.dd[r] = diag_plus_sigma_mask<0>(s2.mask[r], dg, k.one, k.diff_o, k.same_o);
+                    s2.dd[r] = diag_mask_bit<0>(s2.tm, r, dg, k);
                 } else {
                     s2.qc[r] = sm.q[(R * g + r) & QM];
                     s2.dd[r] = diag_plus_sigma(s2.qc[r], sc[0], dg, k.one, k.diff_o, k.same_o);
@@ -531,16 +579,24 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 }
             }
         } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int row = R * g + r;
-                if (!GUARD || (unsigned)row < (unsigned)hb) relax_row(row, xl[r], el[r], mask_cur[r], hr[r], er[r]);
+            const int row0 = R * g;
+            if (!GUARD || (unsigned)row0 < (unsigned)hb)
+                relax_row(std::integral_constant<int, 0>{}, row0, xl[0], el[0], hr[0], er[0]);
+            if constexpr (R > 1) {
+                if ((unsigned)(row0 + 1) < (unsigned)hb)
+                    relax_row(std::integral_constant<int, 1>{}, row0 + 1, xl[R > 1 ? 1 : 0], el[R > 1 ? 1 : 0], hr[R > 1 ? 1 : 0], er[R > 1 ? 1 : 0]);
+            }
+            if constexpr (R > 2) {
+                if ((unsigned)(row0 + 2) < (unsigned)hb)
+                    relax_row(std::integral_constant<int, 2>{}, row0 + 2, xl[R > 2 ? 2 : 0], el[R > 2 ? 2 : 0], hr[R > 2 ? 2 : 0], er[R > 2 ? 2 : 0]);
+                if ((unsigned)(row0 + 3) < (unsigned)hb)
+                    relax_row(std::integral_constant<int, 3>{}, row0 + 3, xl[R > 2 ? 3 : 0], el[R > 2 ? 3 : 0], hr[R > 2 ? 3 : 0], er[R > 2 ? 3 : 0]);
             }
         }
         // also on steps where this lane is still above the band: its first row
-        // must find the mask of row 0 in place
+        // group must find its tile mask in place
 #pragma unroll
-        for (int r = 0; r < R; ++r) mask_cur[r] = mask_next[r];
+        for (int w = 0; w < W; ++w) tm_cur[w] = tm_next[w];
     };
 
 #ifdef ANYSEQ_PROFILE
@@ -607,10 +663,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 qsym = qrow[rn];
             }
             __syncwarp();
-            if constexpr (MASK) {
-#pragma unroll
-                for (int r2 = 0; r2 < R; ++r2) mask_cur[r2] = row_mask(R * (tb - lane) + r2);   // rows of this lane at step tb
-            }
+            if constexpr (MASK) tile_mask(tb - lane, tm_cur);     // row group of this lane at step tb
             PF_END(pf_io);
         }
         PF_BEGIN();
@@ -700,7 +753,7 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
     constexpr int R = StripRows<K, MASK>::value;
     __shared__ WarpSmem s_warp[kWarpsPerBlock];
     __shared__ uint8_t s_lut[MASK ? 512 : 4];
-    extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32] column masks
+    extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32][W] spread column masks
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -712,7 +765,7 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
         }
         __syncthreads();
     }
-    unsigned* s_mask = s_dyn + warp * a.ncodes * 32;
+    unsigned* s_mask = s_dyn + warp * a.ncodes * 32 * TileWords<R, K>::value;
     // the query ring is read one row ahead (mask prefetch): never let an
     // uninitialised byte be used as a code
     for (int x = lane; x < 256; x += 32) s_warp[warp].q[x] = 0;

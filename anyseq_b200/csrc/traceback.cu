@@ -292,7 +292,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         const int nparts = num_halfs / 2;
         const int K = std::max(4, std::min(Ktop, half / kWarp));
         const int SW = kWarp * K;
-        const int resident = resident_warps(K, local, false);
+        const int resident = resident_warps(K, local, false, (n + SW - 1) / SW);
 
         jobs.clear();
         parts.clear();
