@@ -152,6 +152,13 @@ class Aligner:
         self._lib.anyseq_last_splits(self._ctx, buf, n)
         return list(buf[:n])
 
+    def last_split_types(self):
+        """Gotoh traceback: vertex type per split row (0 = H, 1 = E); empty for linear gaps"""
+        n = self._lib.anyseq_last_split_types(self._ctx, None, 0)
+        buf = (C.c_int32 * max(n, 1))()
+        self._lib.anyseq_last_split_types(self._ctx, buf, n)
+        return list(buf[:n])
+
     # -- batches of independent pairs --------------------------------------
     def score_batch(self, mode, queries, q_off, subjects, s_off, scoring: ScoringScheme = REFERENCE_SCORING):
         q, s = as_u8(queries), as_u8(subjects)

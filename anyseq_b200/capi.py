@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
     "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
     "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
-    "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_cigar",
+    "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_last_split_types", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
     "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_strip_combine",
@@ -95,6 +95,8 @@ def load_library(path: str | None = None):
     L.anyseq_align.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, vp, vp, C.POINTER(Result)]
     L.anyseq_last_splits.restype = C.c_int
     L.anyseq_last_splits.argtypes = [vp, C.POINTER(C.c_int32), C.c_int]
+    L.anyseq_last_split_types.restype = C.c_int
+    L.anyseq_last_split_types.argtypes = [vp, C.POINTER(C.c_int32), C.c_int]
     L.anyseq_cigar.restype = C.c_int64
     L.anyseq_cigar.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
     L.anyseq_score_batch.restype = C.c_int

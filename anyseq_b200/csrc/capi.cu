@@ -109,6 +109,15 @@ int anyseq_last_splits(anyseq_ctx* ctx, int32_t* out, int cap)
     return n;
 }
 
+int anyseq_last_split_types(anyseq_ctx* ctx, int32_t* out, int cap)
+{
+    if (!ctx) return ANYSEQ_ERR_BAD_ARG;
+    const std::vector<int>& v = ctx->eng.last_types();
+    const int n = (int)v.size();
+    if (out) for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
 int64_t anyseq_cigar(const char* aq, const char* as, int64_t len, char* out, int64_t cap)
 {
     // derived view (SURVEY.md 8b "Output format"): '=' equal symbols, 'X'

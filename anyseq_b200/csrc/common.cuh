@@ -66,6 +66,8 @@ struct Job {
     int out_tag;
     // initialisation of the borders (init kernel)
     int init_global;         // 1: gap multiples (global), 0: zeros
+    int top_open;            // global: H(-1, j) = top_open + j * gap_extend (cost of the first gap symbol on
+                             // the top border; smaller for Gotoh traceback blocks entered inside a gap)
 };
 
 struct ScoreParams {

@@ -30,12 +30,12 @@ __global__ void init_jobs_kernel(const Job* __restrict__ jobs, int njobs, ScoreP
                 J.col[idx] = make_int4(J.init_global ? sp.gap_open + idx * sp.gap_extend : 0, 0, kNegInf, 0);
             }
             if (idx < wpad) {
-                J.rowH[idx] = J.init_global ? sp.gap_open + (col0 + idx) * sp.gap_extend : 0;
+                J.rowH[idx] = J.init_global ? J.top_open + (col0 + idx) * sp.gap_extend : 0;
                 if (J.rowF) J.rowF[idx] = kNegInf;
             }
             if (idx < J.nstrips) {
                 const int c = col0 + idx * SW - 1;   // column left of the strip
-                J.corner[idx] = (J.init_global && c >= 0) ? sp.gap_open + c * sp.gap_extend : 0;
+                J.corner[idx] = (J.init_global && c >= 0) ? J.top_open + c * sp.gap_extend : 0;
                 J.progress[idx] = 0;
             }
             if (idx == 0 && J.best) *J.best = kScoreMin;
@@ -473,6 +473,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     J.progress = progress_.as<int>();
     J.best = misc_.as<int>() + kMiscBest;
     J.init_global = sc.mode == ANYSEQ_GLOBAL;
+    J.top_open = sp.gap_open;
     // the tag of a run is agreed without communication: both ends count their uses of the inbox
     if (inbox) { J.in = inbox->records; J.in_tag = 0x40000000 + (++inbox->uses_in & 0xffffff); }
     if (next_inbox) { J.out = next_inbox->records; J.out_tag = 0x40000000 + (++next_inbox->uses_out & 0xffffff); }

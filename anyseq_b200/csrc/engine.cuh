@@ -75,6 +75,8 @@ public:
                            Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out);
     int align_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                    char* alq, char* als, anyseq_result* out);
+    int align_host_affine(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                          char* alq, char* als, anyseq_result* out);
     int score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, const int64_t* d_qoff,
                            const uint8_t* d_s, const int64_t* d_soff, int64_t npairs,
                            int32_t* d_scores, anyseq_result* out);
@@ -90,6 +92,7 @@ public:
 
     Tuning tune;
     const std::vector<int>& last_splits() const { return last_splits_; }
+    const std::vector<int>& last_types() const { return last_types_; }
     int device = -1;
     int sm_count = 0;
     char name[64] = {0};
@@ -112,6 +115,7 @@ private:
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
     int* h_misc_ = nullptr;           // pinned mirror of misc_
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
+    std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)
     int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)
     bool use_mask_ = false;
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)

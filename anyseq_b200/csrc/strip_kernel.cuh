@@ -318,7 +318,7 @@ struct CellR {
             s.x[r] = x;
             above_x = x;
             if constexpr (PARTIAL) {
-                if (C == k.outc) s.xs[r] = x;      // E of the matrix's last column has no consumer
+                if (C == k.outc) { s.xs[r] = x; s.es[r] = s.e[r]; }   // E of the last column: Gotoh traceback joins
             }
         }
         if constexpr (LOCAL) {

@@ -196,10 +196,6 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
                        char* als, anyseq_result* out)
 {
     if (m < 0 || n < 0 || !out || (m > 0 && !q) || (n > 0 && !s)) { set_last_error("bad arguments"); return ANYSEQ_ERR_BAD_ARG; }
-    if (sc.gap_init != 0) {
-        set_last_error("linear-space traceback supports linear gaps only (as the reference does)");
-        return ANYSEQ_ERR_UNSUPPORTED;
-    }
     std::lock_guard<std::recursive_mutex> lock(mu_);
     ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
     ScoreParams sp;
@@ -225,6 +221,8 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         return ANYSEQ_OK;
     }
 
+    if (sc.gap_init != 0) return align_host_affine(sc, q, m, s, n, alq, als, out);   // Gotoh: traceback_affine.cu
+    last_types_.clear();
     const bool local = sc.mode == ANYSEQ_LOCAL;
     const int init_global = sc.mode == ANYSEQ_GLOBAL;
     int launches = 0;
@@ -327,6 +325,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
                 strip_total += J.nstrips;
                 J.best = misc_.as<int>() + kMiscBest;
                 J.init_global = init_global;
+                J.top_open = sp.gap_open;
                 jobs.push_back(J);
             }
         }

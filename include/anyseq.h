@@ -120,9 +120,11 @@ int anyseq_score_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                         const void* d_query, int lenq, const void* d_subject, int lens,
                         anyseq_result* out);
 
-/* Linear-space traceback (linear gaps only, like the reference):
- * traceback_lintime of src/align.impala:237-311, bit-exact with the reference
- * CPU build (hb_sum candidate order for BLOCK_WIDTH = 1024).  Output buffers as
+/* Linear-space traceback.  Linear gaps: traceback_lintime of
+ * src/align.impala:237-311, bit-exact with the reference CPU build (hb_sum
+ * candidate order for BLOCK_WIDTH = 1024).  Gotoh gaps (gap_init < 0): the same
+ * driver with Myers-Miller joins -- defined by this build (the reference has no
+ * affine path), optimal for the global scheme; see DESIGN.md.  Output buffers as
  * for construct_*.  out->score is the true optimal score of the scheme. */
 int anyseq_align(anyseq_ctx* ctx, const anyseq_scoring* sc,
                  const char* query, int lenq, const char* subject, int lens,
@@ -133,6 +135,11 @@ int anyseq_align(anyseq_ctx* ctx, const anyseq_scoring* sc,
  * is slot -1 (= 0), then one entry per 128-column block.  Returns the number of
  * entries (writes at most cap). */
 int anyseq_last_splits(anyseq_ctx* ctx, int32_t* out, int cap);
+
+/* Gotoh traceback only: type of every split vertex (0 = ordinary, 1 = a horizontal
+ * gap runs through it), same indexing as anyseq_last_splits; empty after a
+ * linear-gap traceback. */
+int anyseq_last_split_types(anyseq_ctx* ctx, int32_t* out, int cap);
 
 /* Derived view of an alignment pair: CIGAR string (=/X/I/D run-length, I = gap
  * in the query ('_' in alQuery), D = gap in the subject), skipping blank

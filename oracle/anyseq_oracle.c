@@ -662,3 +662,250 @@ uint64_t oracle_fnv1a64(const uint8_t* p, int64_t n)
     for (int64_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
     return h;
 }
+
+/* ========================================================================
+ * Affine (Gotoh) linear-space traceback.  BUILD-DEFINED: the reference has no
+ * affine path at all (src/align.impala:153-166 is an uncalled stub), so
+ * *** parity is unpinned vs the reference ***.  The driver keeps the shape of
+ * traceback_lintime (src/align.impala:237-311: Splits over 128-column blocks,
+ * halves relaxed forward / on reversed sequences, hb_sum candidate scan order,
+ * final blockwise pass + per-block walk); what is new is what Gotoh needs
+ * (Myers & Miller 1988, adapted to splitting the SUBJECT):
+ *   - every half also reports E (horizontal-gap state) at its last column;
+ *   - a split vertex has a type: H (ordinary) or E (a horizontal gap runs
+ *     through it); candidates per row i, scanned H first then E, strict '>':
+ *         H:  LH(i) + RH(len-i-2)
+ *         E:  LE(i) + RE(len-i-2) - gi          (the gap is opened once)
+ *   - a block whose start (end) vertex has type E gets a free gap opening on
+ *     its top border (on the top border of its reversed problem);
+ *   - final blocks keep 4 predecessor bits per cell (H source, E ext, F ext) and
+ *     are walked with a 3-state machine; a block with end type E starts the
+ *     walk in state E if E(end) - gi > H(end).
+ * For the global scheme the result is an optimal Gotoh alignment (tested:
+ * column score under affine costs == textbook optimum).  Semiglobal / local
+ * keep the reference's fragment semantics (zero borders, walk until NONE).
+ * ====================================================================== */
+typedef struct { int32_t* H; int32_t* E; } hecol;
+
+/* Gotoh over rows [0,h) x cols [0,w) of (q,s) read with direction dir from the given
+ * bases; top border opening cost open_top; writes H and E of the last column per row */
+static void affine_half(int mode, const uint8_t* q, int qbase, const uint8_t* s, int sbase, int dir,
+                        int h, int w, int same, int diff, int gi, int ge, int open_top,
+                        int32_t* outH, int32_t* outE)
+{
+    const int glob = mode == ORACLE_GLOBAL, loc = mode == ORACLE_LOCAL;
+    const int go = gi + ge;
+    int32_t* Hrow = (int32_t*)malloc(sizeof(int32_t) * (size_t)(w + 1));
+    int32_t* Frow = (int32_t*)malloc(sizeof(int32_t) * (size_t)(w + 1));
+    for (int j = 0; j < w; ++j) { Hrow[j] = glob ? open_top + (j + 1) * ge : 0; Frow[j] = NEG_INF; }
+    int32_t diag0 = 0;                                   /* H(-1,-1) */
+    for (int i = 0; i < h; ++i) {
+        int32_t hleft = glob ? gi + (i + 1) * ge : 0;    /* H(i,-1) */
+        int32_t e = NEG_INF;
+        int32_t diag = diag0;
+        diag0 = hleft;
+        const uint8_t qc = q[qbase + dir * i];
+        for (int j = 0; j < w; ++j) {
+            const int32_t up = Hrow[j];
+            e = imax(e + ge, hleft + go);
+            const int32_t f = imax(Frow[j] + ge, up + go);
+            int32_t sc = diag + (qc == s[sbase + dir * j] ? same : diff);
+            if (e > sc) sc = e;
+            if (f > sc) sc = f;
+            if (loc && 0 > sc) sc = 0;
+            diag = up; hleft = sc; Hrow[j] = sc; Frow[j] = f;
+        }
+        outH[i] = hleft;
+        outE[i] = e;
+    }
+    free(Hrow); free(Frow);
+}
+
+int32_t oracle_traceback_lintime_affine(int mode,
+                                        const uint8_t* q, int m, const uint8_t* s, int n,
+                                        int same, int diff, int gi, int ge,
+                                        uint8_t* out_q, uint8_t* out_s,
+                                        int32_t* splits_out, int32_t* types_out, int threads)
+{
+    const int glob = mode == ORACLE_GLOBAL, loc = mode == ORACLE_LOCAL;
+    const int MPW = ORACLE_MIN_PART_W;
+    const int go = gi + ge;
+    if (threads < 1) threads = 1;
+    memset(out_q, EMPTY_SYM, (size_t)(m + n));
+    memset(out_s, EMPTY_SYM, (size_t)(m + n));
+
+    int part_width = oracle_next_pow_2(n);
+    splits_t sp;
+    sp.num_blocks = ceil_div(n, MPW);
+    sp.v = ivec_new(sp.num_blocks);
+    sp.bpp = part_width / MPW;
+    V(sp.v, -1) = 0;
+    V(sp.v, sp.num_blocks - 1) = m;
+    ivec vt = ivec_new(sp.num_blocks);           /* vertex types per splits slot: 0 = H, 1 = E */
+
+    int32_t* LH = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m + 1));
+    int32_t* LE = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m + 1));
+    int32_t* RH = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m + 1));
+    int32_t* RE = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m + 1));
+
+    while (part_width > MPW) {
+        const int half = part_width / 2;
+        const int num_halfs = (n + half - 1) / part_width * 2;
+        const int parts = num_halfs / 2;
+        #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+        for (int hh = 0; hh < num_halfs; ++hh) {
+            const int p = hh / 2, left = (hh % 2 == 0);
+            int off, len;
+            splits_dims(&sp, p, &off, &len);
+            const int start_idx = p * sp.bpp - 1;
+            const int end_idx = imin((p + 1) * sp.bpp - 1, sp.num_blocks - 1);
+            const int c_left = 2 * p * half, c_right = c_left + half;
+            const int rhw = imin(half, n - c_right);
+            if (len <= 0) continue;
+            if (left) {
+                const int open_top = V(vt, start_idx) ? 0 : gi;
+                affine_half(mode, q, off, s, c_left, +1, len, half, same, diff, gi, ge, open_top, LH + off, LE + off);
+            } else {
+                const int open_top = V(vt, end_idx) ? 0 : gi;
+                affine_half(mode, q, off + len - 1, s, c_right + rhw - 1, -1, len, rhw, same, diff, gi, ge, open_top,
+                            RH + off, RE + off);
+            }
+        }
+        /* hb_sum with the reference's candidate scan order, two candidates per row (H then E) */
+        const int bw2 = imin(ORACLE_BLOCK_W, half * 2);
+        const int bpp2 = half * 2 / bw2;
+        for (int p = 0; p < parts; ++p) {
+            int off, len;
+            splits_dims(&sp, p, &off, &len);
+            const int start_idx = p * sp.bpp - 1;
+            const int end_idx = imin((p + 1) * sp.bpp - 1, sp.num_blocks - 1);
+            const int rhw = imin(half, n - (2 * p + 1) * half);
+            const int open_l = V(vt, start_idx) ? 0 : gi;       /* top border of the left half */
+            const int open_r = V(vt, end_idx) ? 0 : gi;         /* top border of the reversed right half */
+            int32_t best = ORACLE_SCORE_MIN, bidx = -1, btype = 0;
+            const int32_t* lh = LH + off; const int32_t* le = LE + off;
+            const int32_t* rh = RH + off; const int32_t* re = RE + off;
+            for (int pb = 0; pb < bpp2; ++pb) {
+                int32_t mxv = ORACLE_SCORE_MIN, idx = -1, typ = 0;
+                if (pb == 0 && len > 0) {
+                    /* all rows to the right half: the left half is one horizontal gap */
+                    const int32_t bl = glob ? open_l + half * ge : 0;
+                    mxv = bl + rh[len - 1]; idx = -1; typ = 0;
+                    if (glob) { int32_t v = bl + re[len - 1] - gi; if (v > mxv) { mxv = v; typ = 1; } }
+                    /* all rows to the left half */
+                    const int32_t br = glob ? open_r + rhw * ge : 0;
+                    int32_t v = lh[len - 1] + br;
+                    if (v > mxv) { mxv = v; idx = len - 1; typ = 0; }
+                    if (glob) { v = le[len - 1] + br - gi; if (v > mxv) { mxv = v; idx = len - 1; typ = 1; } }
+                }
+                for (int i = pb; i < len - 1; i += bpp2) {
+                    int32_t v = lh[i] + rh[len - i - 2];
+                    if (v > mxv) { mxv = v; idx = i; typ = 0; }
+                    v = le[i] + re[len - i - 2] - gi;
+                    if (v > mxv) { mxv = v; idx = i; typ = 1; }
+                }
+                if (pb == 0 || mxv > best) { best = mxv; bidx = idx; btype = typ; }
+            }
+            splits_set(&sp, p, off + bidx + 1);
+            V(vt, p * sp.bpp + sp.bpp / 2 - 1) = btype;
+        }
+        part_width /= 2;
+        sp.bpp /= 2;
+    }
+
+    /* final pass: every 128-column block, 4 predecessor bits per cell, 3-state walk */
+    const int nbj = sp.num_blocks;
+    #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (int b = 0; b < nbj; ++b) {
+        int oi, h;
+        splits_dims(&sp, b, &oi, &h);
+        const int start_idx = b * sp.bpp - 1;
+        const int end_idx = imin((b + 1) * sp.bpp - 1, nbj - 1);
+        const int oj = b * MPW;
+        const int w = imin(MPW, n - oj);
+        const int ts = V(vt, start_idx), te = V(vt, end_idx);
+        const int open_top = ts ? 0 : gi;
+        uint8_t* pred = (uint8_t*)malloc((size_t)imax(h, 1) * (size_t)w);
+        int32_t Hrow[ORACLE_MIN_PART_W], Frow[ORACLE_MIN_PART_W];
+        for (int j = 0; j < w; ++j) { Hrow[j] = glob ? open_top + (j + 1) * ge : 0; Frow[j] = NEG_INF; }
+        int32_t diag0 = 0, h_end = (w > 0 && h == 0) ? Hrow[w - 1] : 0, e_end = NEG_INF;
+        for (int i = 0; i < h; ++i) {
+            int32_t hleft = glob ? gi + (i + 1) * ge : 0;
+            int32_t e = NEG_INF, diag = diag0;
+            diag0 = hleft;
+            const uint8_t qc = q[oi + i];
+            for (int j = 0; j < w; ++j) {
+                const int32_t up = Hrow[j];
+                int eext = 0, fext = 0;
+                int32_t eo = hleft + go;
+                if (e + ge > eo) { eo = e + ge; eext = 1; }
+                e = eo;
+                int32_t fo = up + go;
+                if (Frow[j] + ge > fo) { fo = Frow[j] + ge; fext = 1; }
+                int32_t sc = diag + (qc == s[oj + j] ? same : diff);
+                int src = PRED_NO_GAP;
+                if (e > sc) { sc = e; src = PRED_GAP_Q; }
+                if (fo > sc) { sc = fo; src = PRED_GAP_S; }
+                if (loc && 0 > sc) { sc = 0; src = PRED_NONE; }
+                pred[(size_t)i * w + j] = (uint8_t)(src | (eext << 2) | (fext << 3));
+                diag = up; hleft = sc; Hrow[j] = sc; Frow[j] = fo;
+            }
+            h_end = hleft; e_end = e;
+        }
+        /* walk */
+        int i = h - 1, j = w - 1;
+        int state = 0;                                  /* 0 = H, 1 = E, 2 = F */
+        if (te && h > 0 && w > 0 && e_end - gi > h_end) state = 1;
+        const int ob = oi + oj;
+        for (;;) {
+            if (i < 0 && j < 0) break;
+            if (i < 0) {                                /* top border: horizontal gap (global only) */
+                if (!glob) break;
+                out_q[ob + i + j + 1] = GAP_SYM; out_s[ob + i + j + 1] = s[oj + j]; --j; continue;
+            }
+            if (j < 0) {                                /* left border: vertical gap (global only) */
+                if (!glob) break;
+                out_q[ob + i + j + 1] = q[oi + i]; out_s[ob + i + j + 1] = GAP_SYM; --i; continue;
+            }
+            const uint8_t p = pred[(size_t)i * w + j];
+            if (state == 0) {
+                const int src = p & 3;
+                if (src == PRED_NONE) break;
+                if (src == PRED_NO_GAP) {
+                    out_q[ob + i + j + 1] = q[oi + i]; out_s[ob + i + j + 1] = s[oj + j]; --i; --j;
+                } else state = (src == PRED_GAP_Q) ? 1 : 2;
+            } else if (state == 1) {
+                out_q[ob + i + j + 1] = GAP_SYM; out_s[ob + i + j + 1] = s[oj + j];
+                state = ((p >> 2) & 1) ? 1 : 0; --j;
+            } else {
+                out_q[ob + i + j + 1] = q[oi + i]; out_s[ob + i + j + 1] = GAP_SYM;
+                state = ((p >> 3) & 1) ? 2 : 0; --i;
+            }
+        }
+        free(pred);
+    }
+    if (splits_out) for (int k = -1; k < nbj; ++k) splits_out[k + 1] = V(sp.v, k);
+    if (types_out) for (int k = -1; k < nbj; ++k) types_out[k + 1] = V(vt, k);
+    free(LH); free(LE); free(RH); free(RE);
+    ivec_free(sp.v); ivec_free(vt);
+    /* the value the reference-shaped driver returns (never-relaxed scoring object, quirk Q1) */
+    if (glob) return gi + m * ge;
+    if (mode == ORACLE_SEMIGLOBAL) return 0;
+    return ORACLE_SCORE_MIN;
+}
+
+/* affine column score of an emitted alignment (test helper): gap runs cost gi + L*ge */
+int64_t oracle_alignment_column_score_affine(const uint8_t* aq, const uint8_t* as, int len,
+                                             int same, int diff, int gi, int ge)
+{
+    int64_t t = 0;
+    int run = 0;                       /* 0 none, 1 gap in query row, 2 gap in subject row */
+    for (int k = 0; k < len; ++k) {
+        const uint8_t a = aq[k], b = as[k];
+        if (a == EMPTY_SYM && b == EMPTY_SYM) continue;
+        if (a == GAP_SYM) { t += ge + (run == 1 ? 0 : gi); run = 1; }
+        else if (b == GAP_SYM) { t += ge + (run == 2 ? 0 : gi); run = 2; }
+        else { t += (a == b) ? same : diff; run = 0; }
+    }
+    return t;
+}

@@ -87,6 +87,18 @@ int32_t oracle_traceback_lintime(int mode,
                                  uint8_t* out_q, uint8_t* out_s,
                                  int32_t* splits_out, int threads);
 
+/* Gotoh linear-space traceback in the shape of traceback_lintime.  BUILD-DEFINED
+ * (Myers-Miller joins adapted to subject halves, see anyseq_oracle.c);
+ * *** parity unpinned vs the reference ***.  types_out: vertex type per splits
+ * slot (0 = H, 1 = E = a horizontal gap runs through the vertex). */
+int32_t oracle_traceback_lintime_affine(int mode,
+                                        const uint8_t* q, int m, const uint8_t* s, int n,
+                                        int same, int diff, int gap_init, int gap_extend,
+                                        uint8_t* out_q, uint8_t* out_s,
+                                        int32_t* splits_out, int32_t* types_out, int threads);
+int64_t oracle_alignment_column_score_affine(const uint8_t* aq, const uint8_t* as, int len,
+                                             int same, int diff, int gap_init, int gap_extend);
+
 /* reduce_max(): src/utils.impala:30-49 -> src/iteration_cpu.impala:205-250.
  * vec points at logical index 0 (index -1 must be addressable when offset=-1) */
 void oracle_reduce_max(const int32_t* vec, int offset, int length,

@@ -59,6 +59,11 @@ def lib():
     L.oracle_traceback_lintime.restype = C.c_int32
     L.oracle_traceback_lintime.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                            u8p, u8p, i32p, C.c_int]
+    L.oracle_traceback_lintime_affine.restype = C.c_int32
+    L.oracle_traceback_lintime_affine.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  u8p, u8p, i32p, i32p, C.c_int]
+    L.oracle_alignment_column_score_affine.restype = C.c_int64
+    L.oracle_alignment_column_score_affine.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.oracle_reduce_max.restype = None
     L.oracle_reduce_max.argtypes = [i32p, C.c_int, C.c_int, i32p, i32p]
     L.oracle_next_pow_2.restype = C.c_int32
@@ -130,6 +135,27 @@ def traceback_lintime(mode, q, s, same=2, diff=-1, gap=-1, threads=4):
                                          _ptr(oq), _ptr(os_),
                                          splits.ctypes.data_as(C.POINTER(C.c_int32)), threads)
     return ret, oq[:m + n].tobytes(), os_[:m + n].tobytes(), splits
+
+
+def traceback_lintime_affine(mode, q, s, same=2, diff=-1, gap_init=-2, gap_extend=-1, threads=4):
+    """Returns (ret, aligned_q, aligned_s, splits, vertex types).  Build-defined Gotoh traceback."""
+    q, s = _u8(q), _u8(s)
+    m, n = len(q), len(s)
+    oq = np.zeros(max(m + n, 1), dtype=np.uint8)
+    os_ = np.zeros(max(m + n, 1), dtype=np.uint8)
+    nb = (n + 127) // 128
+    splits = np.zeros(nb + 1, dtype=np.int32)
+    types = np.zeros(nb + 1, dtype=np.int32)
+    i32p = C.POINTER(C.c_int32)
+    ret = lib().oracle_traceback_lintime_affine(_mode(mode), _ptr(q), m, _ptr(s), n, same, diff, gap_init, gap_extend,
+                                                _ptr(oq), _ptr(os_), splits.ctypes.data_as(i32p),
+                                                types.ctypes.data_as(i32p), threads)
+    return ret, oq[:m + n].tobytes(), os_[:m + n].tobytes(), splits, types
+
+
+def column_score_affine(aq: bytes, as_: bytes, same=2, diff=-1, gap_init=-2, gap_extend=-1) -> int:
+    a, b = _u8(aq), _u8(as_)
+    return lib().oracle_alignment_column_score_affine(_ptr(a), _ptr(b), len(a), same, diff, gap_init, gap_extend)
 
 
 def reduce_max(vec, offset, length):

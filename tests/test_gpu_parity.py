@@ -349,3 +349,39 @@ def test_batch_reads_vs_windows(aligner, oracle):
             q, s = qd[qo[p]:qo[p + 1]], sd[so[p]:so[p + 1]]
             assert got[p] == aligner.score(mode, q, s, sch).score
         assert info.kernel_ms > 0
+
+
+# --------------------------------------------------------------------------- Gotoh traceback (build-defined)
+@pytest.mark.parametrize("m,n", [(300, 70), (1, 200), (200, 129), (700, 1500), (5000, 9000), (9000, 5000), (2500, 16385),
+                                 (20000, 30000)])
+def test_affine_traceback_vs_oracle(aligner, oracle, m, n):
+    """Gotoh linear-space traceback: bit-exact strings, split rows and vertex types vs the CPU restatement;
+    for the global scheme the emitted alignment is optimal (affine column score == textbook optimum)"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(m * 13 + n)
+    q = _rand(rng, m)
+    if min(m, n) > 100:
+        # mutated copy with block indels so that gaps cross 128-column boundaries
+        parts, p = [], 0
+        while p < m:
+            L = int(rng.integers(40, 300)); parts.append(q[p:p + L]); p += L
+            if rng.random() < 0.6:
+                parts.append(_rand(rng, int(rng.integers(1, 50))))
+            else:
+                p += int(rng.integers(1, 50))
+        s = np.concatenate(parts)
+        s = np.concatenate([s, _rand(rng, max(0, n - len(s)))])[:n]
+        s[rng.integers(0, n, max(1, n // 20))] = ord("A")
+    else:
+        s = _rand(rng, n)
+    for (sa, di, gi, ge) in ((2, -1, -2, -1), (5, -4, -10, -1)):
+        sch = A.affine_scoring_scheme(sa, di, gi, ge)
+        for mode in MODES:
+            r = aligner.align(mode, q, s, sch)
+            ret, aq, as_, sp, ty = oracle.traceback_lintime_affine(mode, q, s, sa, di, gi, ge, threads=8)
+            assert aligner.last_splits() == sp.tolist(), (mode, sch)
+            assert aligner.last_split_types() == ty.tolist(), (mode, sch)
+            assert r.aligned_query == aq and r.aligned_subject == as_, (mode, sch)
+            if mode == "global":
+                opt = oracle.textbook_affine("global", q, s, sa, di, gi, ge)
+                assert oracle.column_score_affine(r.aligned_query, r.aligned_subject, sa, di, gi, ge) == opt == r.score

@@ -147,3 +147,26 @@ def test_golden_fixtures(oracle, golden):
             ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s)
             assert ret == t["ret"] and sp.tolist() == t["splits"]
             assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == t["sha"]
+
+
+def test_affine_traceback_is_optimal_global(oracle):
+    """build-defined Gotoh traceback (parity unpinned vs the reference): for the global scheme the emitted
+    alignment must be a valid optimal one -- de-gapped rows reproduce the inputs and the affine column score
+    equals the independent textbook Gotoh optimum; joins inside horizontal gaps (type E) must occur"""
+    rng = np.random.default_rng(17)
+    etypes = 0
+    for trial in range(25):
+        m = int(rng.integers(200, 1800))
+        q = _rand(rng, m)
+        parts, p = [], 0
+        while p < m:
+            L = int(rng.integers(50, 200)); parts.append(q[p:p + L]); p += L
+            parts.append(_rand(rng, int(rng.integers(5, 60))))
+        s = np.concatenate(parts)
+        for (sa, di, gi, ge) in ((2, -1, -6, -1), (5, -4, -10, -1)):
+            ret, aq, as_, sp, ty = oracle.traceback_lintime_affine("global", q, s, sa, di, gi, ge)
+            assert _degap(aq) == bytes(q) and _degap(as_) == bytes(s)
+            assert oracle.column_score_affine(aq, as_, sa, di, gi, ge) == oracle.textbook_affine("global", q, s, sa, di, gi, ge)
+            assert ret == gi + m * ge
+            etypes += int(ty.sum())
+    assert etypes > 0
