@@ -17,7 +17,8 @@ LIB = os.path.join(OUT, "libanyseq_b200.so")
 CLI = os.path.join(OUT, "align")
 
 LIB_SOURCES = ["engine.cu", "capi.cu", "microbench.cu", "inbox.cu", "traceback.cu", "traceback_affine.cu", "batch.cu",
-               "strip_inst_00.cu", "strip_inst_01.cu", "strip_inst_10.cu", "strip_inst_11.cu"]
+               "strip_inst_00.cu", "strip_inst_01.cu", "strip_inst_10.cu", "strip_inst_11.cu",
+               "strip_inst_10t.cu", "strip_inst_11t.cu"]
 CLI_SOURCES = ["align_main.cpp", "sequence_io.cpp", "alignment_io.cpp"]
 HEADERS = ["common.cuh", "engine.cuh", "strip_kernel.cuh", "strip_inst.inl", "sequence_io.h", "alignment_io.h",
            os.path.join("..", "..", "include", "anyseq.h")]

@@ -70,6 +70,7 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
     else if (n == "blocks_per_sm") t.blocks_per_sm = value;
     else if (n == "watchdog_ms") t.watchdog_ms = value;
     else if (n == "force_generic") t.force_generic = value != 0;
+    else if (n == "local_end_cell") t.local_end_cell = value != 0;
     else if (n == "align_with_score") t.align_with_score = value != 0;
     else {
         set_last_error("unknown option " + n);

@@ -113,21 +113,74 @@ __global__ void finish_score_kernel(const Job* __restrict__ jobs, int mode, int 
     }
 }
 
+// Local end cell by the reference's rule.  The reference keeps one (maximum, position) slot per index
+// INSIDE a block anti-diagonal (slot = block_dia_j, src/scoring_cpu.impala:56-73), updates a slot with
+// strict '>' as the diagonals go by, and get_score_pos() takes the lowest slot holding the overall
+// maximum (src/scoring.impala:103-110 -> reduce_max, src/utils.impala:30-49).  So among the 1024 x 1024
+// blocks that contain the maximum M the winner has the smallest slot, then the smallest diagonal; inside
+// a block the first cell in row-major order (src/scoring_cpu.impala:48-54).  blockmax holds, per block,
+// (value ^ sign, 0xfffff - row-major position) written by the tracking strip kernels.
+__global__ void local_end_cell_kernel(const unsigned long long* __restrict__ blockmax, int nbi, int nbj,
+                                      int* __restrict__ out)
+{
+    __shared__ unsigned long long s_red[32];
+    const long long nblk = (long long)nbi * nbj;
+    auto block_reduce = [&](unsigned long long v, bool want_max) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = want_max ? (u > v ? u : v) : (u < v ? u : v);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = s_red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            const unsigned long long u = s_red[w];
+            v = want_max ? (u > v ? u : v) : (u < v ? u : v);
+        }
+        return v;
+    };
+    unsigned long long top = 0ull;
+    for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+        const unsigned long long v = blockmax[b] >> 32;
+        top = v > top ? v : top;
+    }
+    top = block_reduce(top, true);
+    unsigned long long pick = ~0ull;            // (slot, diagonal) of the winning block
+    for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+        if ((blockmax[b] >> 32) != top) continue;
+        const int bi = (int)(b / nbj), bj = (int)(b % nbj);
+        const int d = bi + bj;
+        const int slot = min(d, nbi - 1) - bi;
+        const unsigned long long key = ((unsigned long long)(unsigned)slot << 32) | (unsigned)d;
+        pick = key < pick ? key : pick;
+    }
+    pick = block_reduce(pick, false);
+    if (threadIdx.x == 0 && top != 0ull) {
+        const int slot = (int)(pick >> 32), d = (int)(pick & 0xffffffffu);
+        const int bi = min(d, nbi - 1) - slot, bj = d - bi;
+        const unsigned pos = 0xfffffu - (unsigned)(blockmax[(size_t)bi * nbj + bj] & 0xfffffu);
+        out[1] = bi * 1024 + (int)(pos >> 10);
+        out[2] = bj * 1024 + (int)(pos & 1023u);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // kernel dispatch (instantiations live in strip_inst_*.cu)
 // ---------------------------------------------------------------------------
 using KernelFn = StripKernelFn;
 
-static KernelFn pick_kernel(bool local, bool affine, int K, bool mask)
+static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool track)
 {
+    if (local && track) return affine ? get_strip_kernel_11t(K, mask) : get_strip_kernel_10t(K, mask);
     if (local) return affine ? get_strip_kernel_11(K, mask) : get_strip_kernel_10(K, mask);
     return affine ? get_strip_kernel_01(K, mask) : get_strip_kernel_00(K, mask);
 }
 
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)
-static int rows_per_step(int K, bool mask)
+static int rows_per_step(int K, bool mask, bool track)
 {
-    if (!mask) return 1;
+    if (!mask || track) return 1;      // end-cell tracking runs on the single-row kernels
     return K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1);
 }
 
@@ -136,10 +189,10 @@ static int rows_per_step(int K, bool mask)
 // than strips: at most one warp works on a strip at a time, the others would only
 // poll and add spread to the progress of the busy ones -- which is what the
 // strip-to-strip pipeline is sensitive to (measured: profiles/).
-static int default_blocks_per_sm(int K, bool mask, int occupancy_max, long long nstrips, int sm_count)
+static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max, long long nstrips, int sm_count)
 {
     int nb = occupancy_max;
-    if (rows_per_step(K, mask) >= 2) {
+    if (rows_per_step(K, mask, track) >= 2) {
         const long long per_round = 4LL * sm_count;              // warps of one CTA per SM
         const int want = (int)std::max<long long>(1, (nstrips + per_round / 2) / per_round);
         nb = std::min(nb, std::min(3, want));
@@ -148,10 +201,10 @@ static int default_blocks_per_sm(int K, bool mask, int occupancy_max, long long 
 }
 
 // dynamic shared memory of the MASK kernels: [warps][ncodes][32 lanes][W words] spread column masks
-static size_t mask_smem_bytes(bool mask, int ncodes, int K)
+static size_t mask_smem_bytes(bool mask, bool track, int ncodes, int K)
 {
     if (!mask) return 0;
-    const int words = std::max(1, rows_per_step(K, mask) * K / 32);
+    const int words = std::max(1, rows_per_step(K, mask, track) * K / 32);
     return sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock * words;
 }
 
@@ -230,6 +283,7 @@ int Engine::init(int dev)
     if ((env = std::getenv("ANYSEQ_WATCHDOG_MS"))) tune.watchdog_ms = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_ALIGN_SCORE"))) tune.align_with_score = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_FORCE_GENERIC"))) tune.force_generic = std::atoi(env) != 0;
+    if ((env = std::getenv("ANYSEQ_LOCAL_END_CELL"))) tune.local_end_cell = std::atoi(env) != 0;
     return ANYSEQ_OK;
 }
 
@@ -238,7 +292,7 @@ void Engine::destroy()
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
                             &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
-                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_};
+                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_, &blockmax_};
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -249,12 +303,12 @@ void Engine::destroy()
 
 int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
-    KernelFn fn = pick_kernel(local, affine, K, use_mask_);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local);
     if (!fn) return 0;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, ncodes_, K)) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, track_, ncodes_, K)) != cudaSuccess) return 0;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, nb, nstrips, sm_count);
+    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, nstrips, sm_count);
     return nb * kWarpsPerBlock * sm_count;
 }
 
@@ -312,7 +366,7 @@ int Engine::pick_band(int m, int nstrips, int resident, int K) const
     if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
     // rows a strip runs behind its left neighbour: lane skew (32 steps of R rows)
     // plus the 32-row publish and fetch batches, plus slack
-    const long long lag = 32LL * rows_per_step(K, use_mask_) + 96;
+    const long long lag = 32LL * rows_per_step(K, use_mask_, track_) + 96;
     const long long window = std::max(1, std::min(resident, nstrips));
     long long target = std::max<long long>(lag * window, 4096);
     if (target >= m) return std::max(32, (m + 31) / 32 * 32);
@@ -340,16 +394,16 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
 #endif
 
-    KernelFn fn = pick_kernel(local, affine, K, use_mask_);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
-    const size_t dyn_smem = mask_smem_bytes(use_mask_, ncodes_, K);
+    const size_t dyn_smem = mask_smem_bytes(use_mask_, track_, ncodes_, K);
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     long long strips_total = 0;
     for (const Job& j : jobs) strips_total += j.nstrips;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, nb, strips_total, sm_count);
+    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, strips_total, sm_count);
     long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
 
@@ -442,6 +496,10 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int w = col_end - col_begin;
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
     const bool local = sc.mode == ANYSEQ_LOCAL;
+    // the end cell of a local alignment needs the whole matrix in one job (reference block grid)
+    const bool track = local && tune.local_end_cell && !inbox && !next_inbox && col_begin == 0 && col_end == n_total;
+    struct TrackScope { bool& t; ~TrackScope() { t = false; } } track_scope{track_};
+    track_ = track;
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     rc = analyse_alphabet(d_q, m, d_s_slice, w);
     if (rc) return rc;
@@ -474,6 +532,14 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     J.best = misc_.as<int>() + kMiscBest;
     J.init_global = sc.mode == ANYSEQ_GLOBAL;
     J.top_open = sp.gap_open;
+    const int nbi = (m + 1023) / 1024, nbj = (w + 1023) / 1024;
+    if (track) {
+        const size_t bytes = sizeof(unsigned long long) * (size_t)nbi * nbj;
+        if (blockmax_.ensure(bytes)) return ANYSEQ_ERR_NO_DEVICE;
+        ANYSEQ_CUDA_CHECK(cudaMemsetAsync(blockmax_.ptr, 0, bytes, stream_));
+        J.blockmax = blockmax_.as<unsigned long long>();
+        J.nbj = nbj;
+    }
     // the tag of a run is agreed without communication: both ends count their uses of the inbox
     if (inbox) { J.in = inbox->records; J.in_tag = 0x40000000 + (++inbox->uses_in & 0xffffff); }
     if (next_inbox) { J.out = next_inbox->records; J.out_tag = 0x40000000 + (++next_inbox->uses_out & 0xffffff); }
@@ -489,6 +555,12 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
                                                   misc_.as<int>() + kMiscOut);
     ANYSEQ_CUDA_CHECK(cudaGetLastError());
     launches += 1;
+    if (track) {
+        local_end_cell_kernel<<<1, 1024, 0, stream_>>>(blockmax_.as<unsigned long long>(), nbi, nbj,
+                                                        misc_.as<int>() + kMiscOut);
+        ANYSEQ_CUDA_CHECK(cudaGetLastError());
+        launches += 1;
+    }
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_, misc_.ptr, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, stream_));
     ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));

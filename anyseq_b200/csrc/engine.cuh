@@ -40,6 +40,7 @@ struct Tuning {
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
     bool force_generic = false;     // never use the MASK kernels (testing)
+    bool local_end_cell = false;    // local scores also report the reference's end cell (single-row kernels)
     bool align_with_score = true;   // anyseq_align also computes the optimal score (one more m*n pass)
 };
 
@@ -113,11 +114,13 @@ private:
     DeviceBuffer col2_;               // second column-record set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
+    DeviceBuffer blockmax_;      // local end-cell tracking: one key per 1024 x 1024 reference block
     int* h_misc_ = nullptr;           // pinned mirror of misc_
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
     std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)
     int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)
     bool use_mask_ = false;
+    bool track_ = false;         // the running score call tracks the local end cell
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
     std::recursive_mutex mu_;
 };

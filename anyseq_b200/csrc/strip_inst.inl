@@ -10,6 +10,23 @@ StripKernelFn ANYSEQ_INST_NAME(int K, bool mask)
 {
     constexpr bool L = ANYSEQ_INST_LOCAL;
     constexpr bool A = ANYSEQ_INST_AFFINE;
+#ifdef ANYSEQ_INST_TRACK
+    if (mask) {
+        switch (K) {
+            case 4: return strip_kernel<L, A, 4, true, true>;
+            case 8: return strip_kernel<L, A, 8, true, true>;
+            case 16: return strip_kernel<L, A, 16, true, true>;
+            case 32: return strip_kernel<L, A, 32, true, true>;
+            default: return nullptr;
+        }
+    }
+    switch (K) {
+        case 4: return strip_kernel<L, A, 4, false, true>;
+        case 8: return strip_kernel<L, A, 8, false, true>;
+        case 16: return strip_kernel<L, A, 16, false, true>;
+        default: return nullptr;
+    }
+#else
     if (mask) {
         switch (K) {
             case 4: return strip_kernel<L, A, 4, true>;
@@ -26,6 +43,7 @@ StripKernelFn ANYSEQ_INST_NAME(int K, bool mask)
         case 32: return strip_kernel<L, A, 32, false>;
         default: return nullptr;
     }
+#endif
 }
 
 }  // namespace anyseq

@@ -197,6 +197,8 @@ struct StepState {
     int best;        // LOCAL: running maximum
     int hprev;       // LOCAL: H of the previous (even) column, folded pairwise with VIMNMX3
     int es;          // PARTIAL: E of the edge column
+    int bpos;        // TRACK: row * K + column (within the item, within the lane) of the first cell attaining best
+    int rowpos;      // TRACK: row * K of the row being relaxed
     unsigned tm[W];  // MASK: tile mask of the lane's current row group
     int qc;          // !MASK: the row's query byte
 };
@@ -225,7 +227,9 @@ __device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int
 // The diagonal term of cell C+1 is formed before X[C] is overwritten, so the
 // old value dies in place and no register moves are needed.
 // RS / RO: the row is row RO of an RS-row group (selects its bits in the tile mask).
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C>
+// TRACK (local scheme, single-row kernels): also remember WHERE the lane's maximum was first reached, in the
+// lane's own row-major order (strict '>'), for the reference's end-cell rule (src/scoring_cpu.impala:48-72).
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C, bool TRACK = false>
 struct Cell {
     template <int KF, int KS, int W>
     static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState<W>& s,
@@ -251,7 +255,9 @@ struct Cell {
             const int tmax = max(s.xleft, up);
             h = LOCAL ? __viaddmax_s32_relu(tmax, k.ge, dd) : __viaddmax_s32(tmax, k.ge, dd);
         }
-        if constexpr (LOCAL) {
+        if constexpr (LOCAL && TRACK) {
+            if ((!PARTIAL || C < k.nvalid) && h > s.best) { s.best = h; s.bpos = s.rowpos + C; }
+        } else if constexpr (LOCAL) {
             if constexpr (PARTIAL) {
                 if (C < k.nvalid) s.best = max(s.best, h);
             } else if constexpr ((C & 1) != 0) {
@@ -263,7 +269,7 @@ struct Cell {
         const int x = AFFINE ? imad_add(h, k.one, k.go) : h;
         X[C] = x;
         s.xleft = x;
-        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1>::run(X, F, sc, s, k);
+        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK>::run(X, F, sc, s, k);
     }
 };
 
@@ -365,7 +371,7 @@ __device__ __forceinline__ void st_record(int4* p, int4 v)
 // don't-care values (dependencies only run left->right, so they never reach a
 // valid cell), the edge column is picked out for the output, and the local
 // maximum is masked.  R = rows per lane and step (PARTIAL items use R = 1).
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R>
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, bool TRACK = false>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
                                              const KernelArgs& a, WarpSmem& sm,
                                              unsigned* __restrict__ s_mask /* [ncodes][32][W] spread column masks */,
@@ -373,6 +379,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                                              const int lane)
 {
     static_assert(R == 1 || R == 2 || R == 4, "rows per step");
+    static_assert(!TRACK || (LOCAL && R == 1), "end-cell tracking: local scheme, single-row kernels");
     constexpr int SW = kWarp * K;
     constexpr int B = 32 / R;              // steps per batch (a batch = 32 rows)
     constexpr int QM = 64 * R - 1;         // query ring mask
@@ -463,8 +470,24 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     int flushed = 0;                       // rows published so far
     StepState<W> st;
     st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.qc = 0;
+    st.bpos = 0; st.rowpos = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) st.tm[w] = 0u;
+    int vbest = kScoreMin;                 // TRACK: value maximum over the flushed block rows
+    // TRACK: fold the lane's (maximum, first position) of the current 1024-row block row into the per-block table;
+    // key order = larger value first, then smaller row-major position inside the 1024 x 1024 block
+    auto flush_track = [&]() {
+        if (st.best > kScoreMin) {
+            const int row = st.bpos / K, c = st.bpos % K;
+            const int absrow = i0 + row, abscol = jl + c;
+            const unsigned pos = ((unsigned)(absrow & 1023) << 10) | (unsigned)(abscol & 1023);
+            const unsigned long long key =
+                ((unsigned long long)((unsigned)st.best ^ 0x80000000u) << 32) | (unsigned long long)(0xfffffu - pos);
+            atomicMax(J.blockmax + (size_t)(absrow >> 10) * J.nbj + (abscol >> 10), key);
+            vbest = max(vbest, st.best);
+        }
+        st.best = kScoreMin;
+    };
 
     // rows [base, base+32) of the out lane's edge -> tagged records (coalesced 16-byte stores, no fence)
     auto flush32 = [&](int base) {
@@ -490,6 +513,10 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     // one row of one lane (single chain): used for R = 1 and for the guarded steps of R > 1
     auto relax_row = [&](auto ro_tag, const int row, const int xl, const int el, int& hro, int& ero) {
         constexpr int RO = decltype(ro_tag)::value;
+        if constexpr (TRACK) {
+            if (((i0 + row) & 1023) == 0) flush_track();      // a new 1024-row block row of the reference starts
+            st.rowpos = row * K;
+        }
         if constexpr (MASK) {
 #pragma unroll
             for (int w = 0; w < W; ++w) st.tm[w] = tm_cur[w];
@@ -501,7 +528,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         dcarry = xl;
         st.xleft = xl;
         st.e = el;
-        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0>::run(X, F, sc, st, k);
+        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK>::run(X, F, sc, st, k);
         hro = st.xleft;
         ero = st.e;
         if constexpr (PARTIAL) {
@@ -707,6 +734,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     }
     if (lane == 0) __stcg(J.corner + strip, dcarry - go);
     if constexpr (LOCAL) {
+        if constexpr (TRACK) { flush_track(); st.best = vbest; }
         int best = st.best;
         if constexpr (!PARTIAL) best = max(best, st.hprev);
 #pragma unroll
@@ -747,10 +775,11 @@ constexpr int strip_min_blocks()
     return K >= 32 ? 4 : (K >= 16 ? 5 : 6);
 }
 
-template <bool LOCAL, bool AFFINE, int K, bool MASK>
-__global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_kernel(const KernelArgs a)
+template <bool LOCAL, bool AFFINE, int K, bool MASK, bool TRACK = false>
+__global__ void __launch_bounds__(kThreads, TRACK ? (K >= 32 ? 4 : (K >= 16 ? 5 : 6)) : strip_min_blocks<K, MASK>())
+strip_kernel(const KernelArgs a)
 {
-    constexpr int R = StripRows<K, MASK>::value;
+    constexpr int R = TRACK ? 1 : StripRows<K, MASK>::value;
     __shared__ WarpSmem s_warp[kWarpsPerBlock];
     __shared__ uint8_t s_lut[MASK ? 512 : 4];
     extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32][W] spread column masks
@@ -785,9 +814,9 @@ __global__ void __launch_bounds__(kThreads, strip_min_blocks<K, MASK>()) strip_k
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)
-            ok = process_item<LOCAL, AFFINE, K, true, MASK, R>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, true, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         else
-            ok = process_item<LOCAL, AFFINE, K, false, MASK, R>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, false, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         if (!ok) return;
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(a.next_item, 1ull);
@@ -801,5 +830,7 @@ StripKernelFn get_strip_kernel_00(int K, bool mask);
 StripKernelFn get_strip_kernel_01(int K, bool mask);
 StripKernelFn get_strip_kernel_10(int K, bool mask);
 StripKernelFn get_strip_kernel_11(int K, bool mask);
+StripKernelFn get_strip_kernel_10t(int K, bool mask);   // local + end-cell tracking
+StripKernelFn get_strip_kernel_11t(int K, bool mask);
 
 }  // namespace anyseq

@@ -106,7 +106,12 @@ int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int block
 
 /* Named options: "cols_per_lane", "band_rows", "blocks_per_sm", "watchdog_ms",
  * "force_generic" (1: byte-register kernels even for small alphabets),
- * "align_with_score" (0: anyseq_align skips the extra score pass). */
+ * "align_with_score" (0: anyseq_align skips the extra score pass),
+ * "local_end_cell" (1: local scores also fill end_i/end_j with the cell the
+ * reference's get_score_pos() reports -- src/scoring.impala:103-110 with the
+ * slot order of src/scoring_cpu.impala:48-73; runs the single-row kernels,
+ * measured 2.29 vs 3.44 TCUPS on the whole-genome pair; default 0: end_i = end_j = -1
+ * for the local scheme). */
 int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value);
 
 /* Score only: score() of src/align.impala:218-235 with host buffers (the call

@@ -95,6 +95,47 @@ def test_score_sweep_vs_oracle(aligner, oracle, K, band, generic):
         aligner.set_option("force_generic", 0)
 
 
+@pytest.mark.parametrize("K,band,generic", [(0, 0, 0), (4, 96, 0), (8, 0, 1), (16, 160, 0), (32, 0, 0), (16, 64, 1)])
+def test_local_end_cell_vs_oracle(aligner, oracle, K, band, generic):
+    """option local_end_cell: the cell get_score_pos() reports for the local scheme (src/scoring.impala:103-110),
+    i.e. the slot order of the 1024 x 1024 block wavefront (src/scoring_cpu.impala:48-73) -- checked on inputs
+    whose maximum occurs in several blocks (planted repeats) and on low-complexity sequences full of ties"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(7 + K + band)
+    aligner.tune(cols_per_lane=K, band_rows=band, watchdog_ms=10000)
+    aligner.set_option("force_generic", generic)
+    aligner.set_option("local_end_cell", 1)
+    pairs = []
+    for (m, n) in [(1, 1), (40, 300), (300, 200), (1024, 1024), (1025, 1030), (2100, 3100), (3100, 2100), (5000, 1500),
+                   (1, 5000), (4200, 4300)]:
+        pairs.append((_rand(rng, m), _rand(rng, n)))
+        pairs.append((_rand(rng, m, ACGT[:2]), _rand(rng, n, ACGT[:2])))          # ties everywhere
+    unit = _rand(rng, 150)
+
+    def planted(total, offsets):
+        a = _rand(rng, total, ACGT[2:] if total % 2 else ACGT[:2])
+        for o in offsets:
+            a[o:o + len(unit)] = unit
+        return a
+    pairs.append((planted(3500, [100, 1500, 2900]), planted(4101, [700, 2300, 3900])))
+    pairs.append((planted(4101, [30, 1100, 2200, 3300]), planted(3500, [3000, 1900, 60])))
+    pairs.append((planted(2301, [1000]), planted(5000, [10, 1034, 2058, 3082, 4106])))
+    schemes = [A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1)]
+    try:
+        for (q, s) in pairs:
+            for sch in schemes:
+                r = aligner.score("local", q, s, sch)
+                if sch.affine:
+                    ref = oracle.score_affine("local", q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                else:
+                    ref = oracle.score_linear("local", q, s, sch.same, sch.diff, sch.gap_extend)
+                assert (r.score, r.end_i, r.end_j) == tuple(ref), (len(q), len(s), sch)
+    finally:
+        aligner.tune(0, 0, 0, 10000)
+        aligner.set_option("force_generic", 0)
+        aligner.set_option("local_end_cell", 0)
+
+
 def test_score_golden_fixtures(aligner, golden):
     import anyseq_b200 as A
     for c in golden["cases"]:
