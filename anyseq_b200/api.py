@@ -184,11 +184,76 @@ class Aligner:
                                                         C.byref(res)))
         return AlignmentResult(res.score, -1, -1, res.kernel_ms, res.kernel_launches)
 
+    def batch_stream(self, mode, scoring: ScoringScheme = REFERENCE_SCORING, cap_pairs: int = 1 << 17,
+                     cap_query_bytes: int = 32 << 20, cap_subject_bytes: int = 32 << 20, slots: int = 3) -> "BatchStream":
+        return BatchStream(self, mode, scoring, cap_pairs, cap_query_bytes, cap_subject_bytes, slots)
+
     # -- roofline denominator ----------------------------------------------
     def measure_int_peak(self, kind: int = 0):
         ops, mhz = C.c_double(), C.c_float()
         self._check(self._lib.anyseq_measure_int_peak(self._ctx, kind, C.byref(ops), C.byref(mhz)))
         return ops.value, mhz.value
+
+
+class BatchStream:
+    """anyseq_batch_stream_*: one producer thread (acquire -> fill -> submit, finally finish) and one
+    consumer thread (collect -> release) run concurrently; the ctypes calls drop the GIL.  Chunk buffers
+    are pinned host memory owned by the stream, exposed as numpy views."""
+
+    def __init__(self, aligner: Aligner, mode, scoring: ScoringScheme, cap_pairs: int, cap_query_bytes: int,
+                 cap_subject_bytes: int, slots: int = 3):
+        self._al, self._lib = aligner, aligner._lib
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        self._h = C.c_void_p()
+        aligner._check(self._lib.anyseq_batch_stream_open(aligner.handle, C.byref(sc), cap_pairs, cap_query_bytes,
+                                                          cap_subject_bytes, slots, C.byref(self._h)))
+
+    @staticmethod
+    def _view(addr, n, dtype):
+        if not addr or n <= 0:
+            return np.zeros(0, dtype=dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype, count=n)
+
+    def acquire(self):
+        """-> (chunk, queries u8 view, q_off i64 view, subjects u8 view, s_off i64 view)"""
+        c = capi.BatchChunk()
+        self._al._check(self._lib.anyseq_batch_stream_acquire(self._h, C.byref(c)))
+        return (c, self._view(c.queries, c.cap_query_bytes, np.uint8),
+                self._view(C.cast(c.q_off, C.c_void_p).value, c.cap_pairs + 1, np.int64),
+                self._view(c.subjects, c.cap_subject_bytes, np.uint8),
+                self._view(C.cast(c.s_off, C.c_void_p).value, c.cap_pairs + 1, np.int64))
+
+    def submit(self, chunk, npairs: int):
+        chunk.npairs = npairs
+        self._al._check(self._lib.anyseq_batch_stream_submit(self._h, C.byref(chunk)))
+
+    def finish(self):
+        self._al._check(self._lib.anyseq_batch_stream_finish(self._h))
+
+    def collect(self):
+        """-> (chunk, scores view valid until release) or None when every chunk has been collected"""
+        c = capi.BatchChunk()
+        rc = self._lib.anyseq_batch_stream_collect(self._h, C.byref(c))
+        if rc == 1:
+            return None
+        self._al._check(rc)
+        return c, self._view(C.cast(c.scores, C.c_void_p).value, c.npairs, np.int32)
+
+    def release(self, chunk):
+        self._al._check(self._lib.anyseq_batch_stream_release(self._h, C.byref(chunk)))
+
+    def stats(self):
+        res = Result()
+        h2d, d2h = C.c_int64(), C.c_int64()
+        self._al._check(self._lib.anyseq_batch_stream_stats(self._h, C.byref(res), C.byref(h2d), C.byref(d2h)))
+        return {"kernel_ms": res.kernel_ms, "kernel_launches": res.kernel_launches, "h2d_bytes": h2d.value,
+                "d2h_bytes": d2h.value}
+
+    def close(self):
+        if self._h:
+            self._lib.anyseq_batch_stream_close(self._h)
+            self._h = C.c_void_p()
 
 
 _default: Aligner | None = None

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = [
     "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
     "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_last_split_types", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
+    "anyseq_batch_stream_open", "anyseq_batch_stream_acquire", "anyseq_batch_stream_submit", "anyseq_batch_stream_finish",
+    "anyseq_batch_stream_collect", "anyseq_batch_stream_release", "anyseq_batch_stream_stats", "anyseq_batch_stream_close",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
     "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_strip_combine",
     "anyseq_measure_int_peak", "anyseq_device_info",
@@ -46,6 +48,14 @@ class StripPartial(C.Structure):
                 ("col_best", C.c_int32), ("col_best_i", C.c_int32),
                 ("local_best", C.c_int32), ("corner", C.c_int32),
                 ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32)]
+
+
+class BatchChunk(C.Structure):
+    _fields_ = [("queries", C.c_void_p), ("q_off", C.POINTER(C.c_int64)),
+                ("subjects", C.c_void_p), ("s_off", C.POINTER(C.c_int64)),
+                ("cap_pairs", C.c_int64), ("cap_query_bytes", C.c_int64), ("cap_subject_bytes", C.c_int64),
+                ("npairs", C.c_int64), ("scores", C.POINTER(C.c_int32)),
+                ("kernel_ms", C.c_float), ("slot", C.c_int32)]
 
 
 class AnyseqError(RuntimeError):
@@ -104,6 +114,18 @@ def load_library(path: str | None = None):
                                      C.POINTER(C.c_int32), C.POINTER(Result)]
     L.anyseq_score_batch_device.restype = C.c_int
     L.anyseq_score_batch_device.argtypes = [vp, C.POINTER(Scoring), vp, vp, vp, vp, C.c_int64, vp, C.POINTER(Result)]
+    L.anyseq_batch_stream_open.restype = C.c_int
+    L.anyseq_batch_stream_open.argtypes = [vp, C.POINTER(Scoring), C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp)]
+    for name in ("acquire", "submit", "collect", "release"):
+        f = getattr(L, "anyseq_batch_stream_" + name)
+        f.restype = C.c_int
+        f.argtypes = [vp, C.POINTER(BatchChunk)]
+    L.anyseq_batch_stream_finish.restype = C.c_int
+    L.anyseq_batch_stream_finish.argtypes = [vp]
+    L.anyseq_batch_stream_stats.restype = C.c_int
+    L.anyseq_batch_stream_stats.argtypes = [vp, C.POINTER(Result), i64p, i64p]
+    L.anyseq_batch_stream_close.restype = None
+    L.anyseq_batch_stream_close.argtypes = [vp]
     L.anyseq_strip_inbox_create.restype = C.c_int
     L.anyseq_strip_inbox_create.argtypes = [vp, C.c_int, C.POINTER(vp), vp]
     L.anyseq_strip_inbox_open.restype = C.c_int

@@ -10,14 +10,22 @@
 // traceback).  -o is documented by the reference's README (README.md:41,46) but
 // disabled in its source; it is enabled here.  Random inputs follow the
 // reference recipe (default-seeded std::mt19937_64, query first).
+//
+// Addition: align (-b|--batch) <reads file> <windows file> pairs record k of the first
+// file with record k of the second and streams them through anyseq_batch_stream_*: a reader thread
+// parses FASTA/FASTQ records straight into pinned chunk buffers while the GPU scores the previous
+// chunk; one line "<index>\t<score>" per pair.  --mode/--same/--diff/--gap-init/--gap-extend pick
+// the scheme (default: the reference's linear 2/-1/-1, global).
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "anyseq.h"
@@ -81,16 +89,100 @@ std::string random_dna(std::int64_t lo, std::int64_t hi, Rng& rng)
     return out;
 }
 
+// producer: records -> pinned chunk buffers; consumer: scores -> os
+int run_batch(const std::string& reads, const std::string& windows, const anyseq_scoring& sc, std::ostream& os)
+{
+    anyseq_ctx* ctx = nullptr;
+    if (anyseq_ctx_create(-1, &ctx) != ANYSEQ_OK) { std::cerr << anyseq_last_error() << std::endl; return 1; }
+    std::unique_ptr<anyseq_host::SequenceReader> rq, rs;
+    try {
+        rq = anyseq_host::make_sequence_reader(reads);
+        rs = anyseq_host::make_sequence_reader(windows);
+    } catch (std::exception& e) {
+        std::cerr << e.what() << std::endl;
+        anyseq_ctx_destroy(ctx);
+        return 1;
+    }
+    const std::int64_t cap_pairs = 1 << 17, cap_bytes = 48 << 20;
+    anyseq_batch_stream* st = nullptr;
+    if (anyseq_batch_stream_open(ctx, &sc, cap_pairs, cap_bytes, cap_bytes, 3, &st) != ANYSEQ_OK) {
+        std::cerr << anyseq_last_error() << std::endl;
+        anyseq_ctx_destroy(ctx);
+        return 1;
+    }
+    std::string producer_error;
+    std::thread producer([&] {
+        try {
+            anyseq_host::SequenceRecord a, b;
+            bool have = false;
+            for (;;) {
+                anyseq_batch_chunk c;
+                if (anyseq_batch_stream_acquire(st, &c) != ANYSEQ_OK) break;
+                std::int64_t np = 0, nq = 0, ns = 0;
+                c.q_off[0] = c.s_off[0] = 0;
+                for (;;) {
+                    if (!have) {
+                        if (!rq->has_next() || !rs->has_next()) break;
+                        a = rq->next();
+                        b = rs->next();
+                        have = true;
+                    }
+                    const std::int64_t la = static_cast<std::int64_t>(a.data.size()), lb = static_cast<std::int64_t>(b.data.size());
+                    if (la > c.cap_query_bytes || lb > c.cap_subject_bytes)
+                        throw anyseq_host::io_error("record " + std::to_string(a.index) + " is too long for the batch path");
+                    if (np == c.cap_pairs || nq + la > c.cap_query_bytes || ns + lb > c.cap_subject_bytes) break;
+                    std::copy(a.data.begin(), a.data.end(), c.queries + nq);
+                    std::copy(b.data.begin(), b.data.end(), c.subjects + ns);
+                    nq += la; ns += lb; ++np;
+                    c.q_off[np] = nq; c.s_off[np] = ns;
+                    have = false;
+                }
+                c.npairs = np;
+                if (anyseq_batch_stream_submit(st, &c) != ANYSEQ_OK) { producer_error = anyseq_last_error(); break; }
+                if (np == 0 || (!have && (!rq->has_next() || !rs->has_next()))) break;
+            }
+        } catch (std::exception& e) {
+            producer_error = e.what();
+        }
+        anyseq_batch_stream_finish(st);
+    });
+    std::int64_t index = 0;
+    int rc = 0;
+    for (;;) {
+        anyseq_batch_chunk c;
+        const int r = anyseq_batch_stream_collect(st, &c);
+        if (r == ANYSEQ_EOF) break;
+        if (r != ANYSEQ_OK) { std::cerr << anyseq_last_error() << std::endl; rc = 1; break; }
+        for (std::int64_t k = 0; k < c.npairs; ++k) os << ++index << '\t' << c.scores[k] << '\n';
+        anyseq_batch_stream_release(st, &c);
+    }
+    if (rc) {
+        // unblock a producer that waits for a free slot: drain whatever it still submits
+        anyseq_batch_chunk c;
+        while (anyseq_batch_stream_collect(st, &c) == ANYSEQ_OK) anyseq_batch_stream_release(st, &c);
+    }
+    producer.join();
+    if (!producer_error.empty()) { std::cerr << producer_error << std::endl; rc = 1; }
+    os << std::flush;
+    anyseq_batch_stream_close(st);
+    anyseq_ctx_destroy(ctx);
+    return rc;
+}
+
 void usage(const char* argv0)
 {
     std::cout << "SYNOPSIS\n"
               << "        " << argv0 << " [-o <file>] [-p] (-i|--in) <query file> <subject file>\n"
-              << "        " << argv0 << " [-o <file>] [-p] (-r|--rand) [<min len>] [<max len>]\n\n"
+              << "        " << argv0 << " [-o <file>] [-p] (-r|--rand) [<min len>] [<max len>]\n"
+              << "        " << argv0 << " [-o <file>] [scheme] (-b|--batch) <reads file> <windows file>\n\n"
               << "OPTIONS\n"
               << "        -i, --in    read sequences from input files (first record of each)\n"
               << "        -r, --rand  generate random input sequences\n"
               << "        -o, --out   write results to file\n"
-              << "        -p, --print print the alignments (print_alignment format)\n";
+              << "        -p, --print print the alignments (print_alignment format)\n"
+              << "        -b, --batch score record k of the first file against record k of the second\n"
+              << "        scheme:     [--mode global|semiglobal|local] [--same <n>] [--diff <n>]\n"
+              << "                    [--gap-init <n>] [--gap-extend <n>]   (default: global 2 -1 0 -1)\n";
 }
 
 bool parse_int(const std::string& a, std::int64_t* v)
@@ -107,7 +199,8 @@ bool parse_int(const std::string& a, std::int64_t* v)
 
 int main(int argc, char* argv[])
 {
-    enum class Input { none, file, random } input = Input::none;
+    enum class Input { none, file, random, batch } input = Input::none;
+    anyseq_scoring sc = {ANYSEQ_GLOBAL, 2, -1, 0, -1};
     std::string query, subject, outfile;
     std::int64_t minlen = 256, maxlen = 1024;     // reference defaults (src/main.cpp:134-135)
     bool print = false, bad = false, want_out = false;
@@ -123,6 +216,22 @@ int main(int argc, char* argv[])
         } else if ((a == "-i" || a == "--in") && input == Input::none) {
             input = Input::file;
             if (k + 2 < argc) { query = argv[++k]; subject = argv[++k]; } else bad = true;
+        } else if ((a == "-b" || a == "--batch") && input == Input::none) {
+            input = Input::batch;
+            if (k + 2 < argc) { query = argv[++k]; subject = argv[++k]; } else bad = true;
+        } else if (a == "--mode" && k + 1 < argc) {
+            const std::string m = argv[++k];
+            if (m == "global") sc.mode = ANYSEQ_GLOBAL;
+            else if (m == "semiglobal") sc.mode = ANYSEQ_SEMIGLOBAL;
+            else if (m == "local") sc.mode = ANYSEQ_LOCAL;
+            else bad = true;
+        } else if ((a == "--same" || a == "--diff" || a == "--gap-init" || a == "--gap-extend") && k + 1 < argc) {
+            std::int64_t v;
+            if (!parse_int(argv[++k], &v)) bad = true;
+            else if (a == "--same") sc.same = static_cast<int32_t>(v);
+            else if (a == "--diff") sc.diff = static_cast<int32_t>(v);
+            else if (a == "--gap-init") sc.gap_init = static_cast<int32_t>(v);
+            else sc.gap_extend = static_cast<int32_t>(v);
         } else if ((a == "-r" || a == "--rand") && input == Input::none) {
             input = Input::random;
             std::int64_t v;
@@ -140,6 +249,16 @@ int main(int argc, char* argv[])
         }
         usage(argv[0]);
         return 0;                                  // the reference exits 0 here (src/main.cpp:166-174)
+    }
+
+    if (input == Input::batch) {
+        if (want_out) {
+            if (outfile.empty()) { std::cerr << "No output file name given!" << std::endl; return 1; }
+            std::ofstream os(outfile);
+            if (!os.good()) { std::cerr << "Unable to open output file!" << std::endl; return 1; }
+            return run_batch(query, subject, sc, os);
+        }
+        return run_batch(query, subject, sc, std::cout);
     }
 
     if (input == Input::file) {

@@ -318,26 +318,4 @@ int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, con
     return ANYSEQ_OK;
 }
 
-int Engine::score_batch_host(const anyseq_scoring& sc, const char* q, const int64_t* qoff, const char* s,
-                             const int64_t* soff, int64_t npairs, int32_t* scores, anyseq_result* out)
-{
-    std::lock_guard<std::recursive_mutex> lock(mu_);
-    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
-    if (npairs == 0) { if (out) std::memset(out, 0, sizeof(*out)); return ANYSEQ_OK; }
-    const size_t nq = (size_t)qoff[npairs], ns = (size_t)soff[npairs], no = sizeof(int64_t) * (size_t)(npairs + 1);
-    if (batch_q_.ensure(nq + 64) || batch_s_.ensure(ns + 64) || batch_qoff_.ensure(no) || batch_soff_.ensure(no) ||
-        batch_scores_.ensure(sizeof(int32_t) * (size_t)npairs))
-        return ANYSEQ_ERR_NO_DEVICE;
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(batch_q_.ptr, q, nq, cudaMemcpyHostToDevice, stream_));
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(batch_s_.ptr, s, ns, cudaMemcpyHostToDevice, stream_));
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(batch_qoff_.ptr, qoff, no, cudaMemcpyHostToDevice, stream_));
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(batch_soff_.ptr, soff, no, cudaMemcpyHostToDevice, stream_));
-    int rc = score_batch_device(sc, batch_q_.as<uint8_t>(), batch_qoff_.as<int64_t>(), batch_s_.as<uint8_t>(),
-                                batch_soff_.as<int64_t>(), npairs, batch_scores_.as<int32_t>(), out);
-    if (rc) return rc;
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(scores, batch_scores_.ptr, sizeof(int32_t) * (size_t)npairs, cudaMemcpyDeviceToHost, stream_));
-    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    return ANYSEQ_OK;
-}
-
 }  // namespace anyseq

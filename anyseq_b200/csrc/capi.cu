@@ -9,9 +9,6 @@ namespace anyseq {
 const char* last_error_cstr();
 }
 
-struct anyseq_ctx {
-    anyseq::Engine eng;
-};
 struct anyseq_inbox {
     anyseq::Inbox box;
 };
@@ -71,6 +68,9 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
     else if (n == "watchdog_ms") t.watchdog_ms = value;
     else if (n == "force_generic") t.force_generic = value != 0;
     else if (n == "local_end_cell") t.local_end_cell = value != 0;
+    else if (n == "batch_chunk_bytes" && value >= (1 << 16)) t.batch_chunk_bytes = value;
+    else if (n == "batch_chunk_pairs" && value >= 1) t.batch_chunk_pairs = value;
+    else if (n == "batch_copy_threads" && value >= 1) t.batch_copy_threads = value;
     else if (n == "align_with_score") t.align_with_score = value != 0;
     else {
         set_last_error("unknown option " + n);

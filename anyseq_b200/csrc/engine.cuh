@@ -41,7 +41,10 @@ struct Tuning {
     int watchdog_ms = 20000;
     bool force_generic = false;     // never use the MASK kernels (testing)
     bool local_end_cell = false;    // local scores also report the reference's end cell (single-row kernels)
-    bool align_with_score = true;   // anyseq_align also computes the optimal score (one more m*n pass)
+    bool align_with_score = true;
+    int batch_chunk_bytes = 64 << 20;    // host batches: packed symbols per pipeline chunk
+    int batch_chunk_pairs = 1 << 18;     // host batches: pairs per pipeline chunk
+    int batch_copy_threads = 4;          // host batches: threads staging caller memory into pinned slots   // anyseq_align also computes the optimal score (one more m*n pass)
 };
 
 // word layout of the small device "misc" block
@@ -98,6 +101,7 @@ public:
     int sm_count = 0;
     char name[64] = {0};
     int resident_warps(int K, bool local, bool affine, long long nstrips = 1LL << 40);
+    cudaStream_t stream() const { return stream_; }
 
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
@@ -129,3 +133,8 @@ void set_last_error(const std::string& s);
 int make_score_params(const anyseq_scoring& sc, ScoreParams* sp, bool* affine);
 
 }  // namespace anyseq
+
+// the opaque context of the C ABI (include/anyseq.h)
+struct anyseq_ctx {
+    anyseq::Engine eng;
+};

@@ -26,30 +26,123 @@ def column_slices(n: int, world: int, align: int = 1024):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+# ---------------------------------------------------------------------------
+# batches of independent pairs: contiguous ranges per rank, no data-path collective
+# ---------------------------------------------------------------------------
+def pair_ranges(npairs: int, world: int):
+    """contiguous, near-equal ranges of pair ids, one per rank"""
+    return [(npairs * r // world, npairs * (r + 1) // world) for r in range(world)]
+
+
+def shard_batch(q_off, s_off, rank: int, world: int):
+    """-> (p0, p1, byte range of the queries, byte range of the subjects, rebased offsets) of this rank"""
+    import numpy as np
+    qo = np.asarray(q_off, dtype=np.int64)
+    so = np.asarray(s_off, dtype=np.int64)
+    p0, p1 = pair_ranges(len(qo) - 1, world)[rank]
+    return p0, p1, (int(qo[p0]), int(qo[p1])), (int(so[p0]), int(so[p1])), qo[p0:p1 + 1] - qo[p0], so[p0:p1 + 1] - so[p0]
+
+
+def score_batch_sharded(aligner: Aligner, dist, rank: int, world: int, mode, queries, q_off, subjects, s_off,
+                        scoring: ScoringScheme, gather: bool = True):
+    """every rank scores its contiguous range of pairs on its own GPU; the only communication is the
+    gather of the int32 scores at the end (gather=False: each rank keeps just its range)"""
+    import numpy as np
+    p0, p1, (qa, qb), (sa, sb), qo, so = shard_batch(q_off, s_off, rank, world)
+    local, res = aligner.score_batch(mode, capi.as_u8(queries)[qa:qb], qo, capi.as_u8(subjects)[sa:sb], so, scoring)
+    if not gather or world == 1:
+        return local, res
+    parts = [None] * world
+    dist.all_gather_object(parts, local.tobytes())
+    return np.concatenate([np.frombuffer(b, dtype=np.int32) for b in parts]), res
+
+
+class RunTokens:
+    """Host-side flow control between neighbouring ranks for back-to-back runs.
+
+    Run k of rank r streams its right border into inbox k % depth of rank r + 1, so it must not
+    start before rank r + 1 has FINISHED run k - depth (the previous user of those rows).  Rank
+    r + 1 says so with a token (the run index, one int64) sent to rank r after every run; rank r
+    receives the token of run k - depth before it starts run k.  With depth >= 2 the wait is
+    already satisfied in steady state and consecutive alignments overlap: rank 0 starts the next
+    pair while the wavefront of the previous one is still travelling through the later ranks.
+    `group` must be a CPU (gloo) group: tokens never touch a GPU stream."""
+
+    def __init__(self, dist, group, rank: int, world: int, depth: int):
+        import torch
+        self._torch = torch
+        self.dist, self.group, self.rank, self.world, self.depth = dist, group, rank, world, depth
+        self._pending = []
+
+    def acquire(self, k: int):
+        if self.world > 1 and self.rank < self.world - 1 and k >= self.depth:
+            t = self._torch.zeros(1, dtype=self._torch.int64)
+            self.dist.recv(t, src=self.rank + 1, group=self.group)
+            if int(t.item()) != k - self.depth:
+                raise RuntimeError(f"run token out of order: got {int(t.item())}, expected {k - self.depth}")
+
+    def release(self, k: int):
+        if self.world > 1 and self.rank > 0:
+            t = self._torch.full((1,), k, dtype=self._torch.int64)
+            self._pending.append((self.dist.isend(t, dst=self.rank - 1, group=self.group), t))
+            self._pending = [(w, t) for (w, t) in self._pending if not w.is_completed()]
+
+    def drain(self, runs: int):
+        """receive the tokens nobody waited for (end of a stream of `runs` runs; every rank calls it)"""
+        if self.world > 1 and self.rank < self.world - 1:
+            for k in range(max(0, runs - self.depth), runs):
+                t = self._torch.zeros(1, dtype=self._torch.int64)
+                self.dist.recv(t, src=self.rank + 1, group=self.group)
+        for (w, _) in self._pending:
+            w.wait()
+        self._pending = []
+
+
 class StripWavefront:
-    def __init__(self, aligner: Aligner, rank: int, world: int, rows: int, dist=None):
+    """depth = number of inboxes per rank boundary.  depth 1: every rank must have finished run k
+    before any rank starts run k + 1 (the caller puts a barrier between runs).  depth >= 2:
+    back-to-back runs are flow-controlled by RunTokens and overlap (no barrier between runs)."""
+
+    def __init__(self, aligner: Aligner, rank: int, world: int, rows: int, dist=None, depth: int = 1):
         self.al, self.rank, self.world, self.rows, self.dist = aligner, rank, world, rows, dist
+        self.depth = max(1, int(depth)) if world > 1 else 1
         self._lib = capi.load_library()
-        self.inbox = C.c_void_p()
-        self.next_inbox = C.c_void_p()
-        handle = (C.c_ubyte * 64)()
-        if world > 1 and rank > 0:
-            aligner._check(self._lib.anyseq_strip_inbox_create(aligner.handle, rows, C.byref(self.inbox), handle))
-        if world > 1:
-            handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle))
-            if rank < world - 1:
-                buf = (C.c_ubyte * 64).from_buffer_copy(handles[rank + 1])
-                aligner._check(self._lib.anyseq_strip_inbox_open(aligner.handle, buf, rows, C.byref(self.next_inbox)))
+        self.inboxes = [C.c_void_p() for _ in range(self.depth)]
+        self.next_inboxes = [C.c_void_p() for _ in range(self.depth)]
+        self.k = 0
+        self.tokens = None
+        for d in range(self.depth):
+            handle = (C.c_ubyte * 64)()
+            if world > 1 and rank > 0:
+                aligner._check(self._lib.anyseq_strip_inbox_create(aligner.handle, rows, C.byref(self.inboxes[d]), handle))
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, bytes(handle))
+                if rank < world - 1:
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[rank + 1])
+                    aligner._check(self._lib.anyseq_strip_inbox_open(aligner.handle, buf, rows, C.byref(self.next_inboxes[d])))
+        if world > 1 and self.depth > 1:
+            self.tokens = RunTokens(dist, dist.new_group(backend="gloo"), rank, world, self.depth)
+
+    # single-inbox views (depth 1 users)
+    @property
+    def inbox(self):
+        return self.inboxes[0]
+
+    @property
+    def next_inbox(self):
+        return self.next_inboxes[0]
 
     def reset(self):
         """re-synchronise the run counters of both ends of every inbox and clear the owned
-        one; every rank must call it (ends with a barrier).  Not needed between runs: border
+        ones; every rank must call it (ends with a barrier).  Not needed between runs: border
         records carry a per-run tag."""
-        if self.inbox:
-            self.al._check(self._lib.anyseq_strip_inbox_reset(self.al.handle, self.inbox))
-        if self.next_inbox:
-            self.al._check(self._lib.anyseq_strip_inbox_reset(self.al.handle, self.next_inbox))
+        if self.tokens is not None:
+            self.tokens.drain(self.k)
+        for h in self.inboxes + self.next_inboxes:
+            if h:
+                self.al._check(self._lib.anyseq_strip_inbox_reset(self.al.handle, h))
+        self.k = 0
         if self.world > 1:
             self.dist.barrier()
 
@@ -57,10 +150,16 @@ class StripWavefront:
             col_begin: int, col_end: int, n_total: int) -> StripPartial:
         sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
         part = StripPartial()
+        k = self.k
+        inbox, nxt = self.inboxes[k % self.depth], self.next_inboxes[k % self.depth]
+        if self.tokens is not None:
+            self.tokens.acquire(k)
         self.al._check(self._lib.anyseq_score_strip_device(
             self.al.handle, C.byref(sc), C.c_void_p(d_query), m, C.c_void_p(d_subject_slice),
-            col_begin, col_end, n_total, self.inbox if self.inbox else None,
-            self.next_inbox if self.next_inbox else None, C.byref(part)))
+            col_begin, col_end, n_total, inbox if inbox else None, nxt if nxt else None, C.byref(part)))
+        if self.tokens is not None:
+            self.tokens.release(k)
+        self.k = k + 1
         return part
 
     def combine(self, mode, scoring: ScoringScheme, part: StripPartial) -> AlignmentResult:
@@ -76,9 +175,11 @@ class StripWavefront:
         return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches)
 
     def close(self):
-        if self.inbox:
-            self._lib.anyseq_strip_inbox_destroy(self.al.handle, self.inbox)
-            self.inbox = C.c_void_p()
-        if self.next_inbox:
-            self._lib.anyseq_strip_inbox_destroy(self.al.handle, self.next_inbox)
-            self.next_inbox = C.c_void_p()
+        if self.tokens is not None:
+            self.tokens.drain(self.k)
+            self.k = 0
+        for lst in (self.inboxes, self.next_inboxes):
+            for i, h in enumerate(lst):
+                if h:
+                    self._lib.anyseq_strip_inbox_destroy(self.al.handle, h)
+                    lst[i] = C.c_void_p()

@@ -168,6 +168,8 @@ def main():
                          "150000 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="N > 1: barrier between steps (every alignment pays the full wavefront fill)")
     args = ap.parse_args()
     _claim_stdout()
 
@@ -210,15 +212,18 @@ def main():
     d_q = h_q.cuda()
     d_s = h_s.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    wave = StripWavefront(al, rank, world, m, dist)
+    # N > 1: two inboxes per rank boundary, so consecutive alignments stream through the ranks back to
+    # back (rank 0 starts pair k+1 while the wavefront of pair k is still inside the later ranks); the
+    # neighbour-to-neighbour run tokens of multigpu.RunTokens replace a barrier between steps
+    wave = StripWavefront(al, rank, world, m, dist, depth=1 if args.no_pipeline else 2)
     torch.cuda.synchronize()
 
     wave.reset()
 
-    def step_resident():
+    def step_resident(isolated=False):
         flush.zero_()
-        if dist is not None:
-            dist.barrier()          # every rank has finished the previous run (inbox rows may be rewritten)
+        if dist is not None and (isolated or args.no_pipeline):
+            dist.barrier()          # every rank has finished the previous run
         torch.cuda.synchronize()
         part = wave.run(MODE, scoring, d_q.data_ptr(), m, d_s.data_ptr(), c0, c1, n)
         return part
@@ -227,21 +232,30 @@ def main():
     for _ in range(args.warmup):
         part = step_resident()
     sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
         sampler.start()
     t_wall0 = time.perf_counter()
+    ev0.record()
     dev_ms = 0.0
     launches = 0
     for _ in range(args.steps):
         part = step_resident()
         dev_ms += part.kernel_ms
         launches += part.kernel_launches
+    # wave.run() returns after its kernels have finished (the call synchronises its stream), so an event
+    # on the idle torch stream is a device timestamp of "this rank's last step is done"
+    ev1.record()
+    ev1.synchronize()
+    span_ms = ev0.elapsed_time(ev1)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     res = wave.combine(MODE, scoring, part)
-    t = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    if world == 1:
+        span_ms = dev_ms           # one rank: the sum of the per-call CUDA-event times (excludes the L2 flush)
+    t = torch.tensor([span_ms, t_wall * 1e3], dtype=torch.float64, device="cuda")
     lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -249,6 +263,16 @@ def main():
     dev_ms_max, wall_ms_max = t.tolist()
     ms_per_step = dev_ms_max / args.steps
     value = cells / (ms_per_step * 1e-3) / 1e9
+
+    # latency of ONE alignment across the ranks (barrier before it, max over ranks of the call's event time)
+    single_ms = None
+    if world > 1:
+        lat = []
+        for _ in range(2):
+            lat.append(step_resident(isolated=True).kernel_ms)
+        tl = torch.tensor([min(lat)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        single_ms = tl.item()
 
     # ---- e2e: host buffers through the public API --------------------------------
     e2e = None
@@ -260,8 +284,6 @@ def main():
                 # the reference-facing C ABI call with HOST pointers: H2D of both
                 # sequences, kernels, D2H of the result, all inside the call
                 return al.score(MODE, h_q.numpy(), h_s.numpy(), scoring).score
-            if dist is not None:
-                dist.barrier()
             dq = h_q.cuda(non_blocking=True)
             ds = h_s.cuda(non_blocking=True)
             torch.cuda.synchronize()
@@ -328,7 +350,14 @@ def main():
                    "rows": m, "cols": n, "cells_per_step": cells,
                    "partition": f"{world} column strip(s), boundary column streamed over NVLink" if world > 1 else "1 GPU",
                    "l2": "L2 flushed (256 MiB memset) before every timed step",
-                   "timing": "CUDA events on the library's launch stream, summed over steps, max over ranks"},
+                   "timing": ("CUDA events on the library's launch stream, summed over steps" if world == 1 else
+                              "CUDA events around the K steps on every rank, max over ranks"),
+                   "steps_overlap": (None if world == 1 else
+                                     ("no: barrier between steps" if args.no_pipeline else
+                                      "yes: consecutive alignments stream through the ranks back to back (double inboxes + "
+                                      "neighbour run tokens); single_alignment_ms is one alignment alone, barrier before it")),
+                   "single_alignment_ms": single_ms,
+                   "single_alignment_gcups": (cells / (single_ms * 1e-3) / 1e9) if single_ms else None},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "score": int(res.score),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()),

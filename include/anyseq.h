@@ -63,6 +63,7 @@ enum {                       /* alignment schemes: src/align.impala:96-124 */
 };
 
 enum {                       /* status codes (0 = ok, < 0 = failure) */
+    ANYSEQ_EOF = 1,          /* anyseq_batch_stream_collect: every submitted chunk has been collected */
     ANYSEQ_OK = 0,
     ANYSEQ_ERR_NO_DEVICE = -1,
     ANYSEQ_ERR_BAD_ARG = -2,
@@ -107,6 +108,8 @@ int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int block
 /* Named options: "cols_per_lane", "band_rows", "blocks_per_sm", "watchdog_ms",
  * "force_generic" (1: byte-register kernels even for small alphabets),
  * "align_with_score" (0: anyseq_align skips the extra score pass),
+ * "batch_chunk_bytes" / "batch_chunk_pairs" / "batch_copy_threads" (pipeline of
+ * anyseq_score_batch with host buffers),
  * "local_end_cell" (1: local scores also fill end_i/end_j with the cell the
  * reference's get_score_pos() reports -- src/scoring.impala:103-110 with the
  * slot order of src/scoring_cpu.impala:48-73; runs the single-row kernels,
@@ -163,6 +166,39 @@ int anyseq_score_batch_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                               const void* d_queries, const int64_t* d_q_off,
                               const void* d_subjects, const int64_t* d_s_off,
                               int64_t npairs, int32_t* d_scores, anyseq_result* out);
+
+/* Streaming batches (many-record FASTA/FASTQ x windows ingestion that is not H2D-bound).
+ * A stream owns `slots` chunk slots of PINNED host memory + device memory.  One producer thread
+ *   acquire (blocks for a free slot) -> fill queries/q_off/subjects/s_off/npairs -> submit (starts H2D)
+ * and one consumer thread
+ *   collect (next chunk in submission order: kernel + D2H of the scores; ANYSEQ_EOF after finish)
+ *   -> use chunk.scores -> release (slot becomes free)
+ * run concurrently, so parsing/copying chunk c+1 overlaps the kernel of chunk c.  The reference's host
+ * reader has the same producer/consumer shape (next()/skip() under a mutex, src/sequence_io.cpp:13-41).
+ * anyseq_score_batch() with host buffers is a stream fed from the caller's arrays.  Offsets of a chunk
+ * are chunk-relative (q_off[0] == s_off[0] == 0). */
+typedef struct anyseq_batch_stream anyseq_batch_stream;
+typedef struct anyseq_batch_chunk {
+    char* queries;             /* acquire: pinned buffer of cap_query_bytes */
+    int64_t* q_off;            /* acquire: cap_pairs + 1 offsets */
+    char* subjects;
+    int64_t* s_off;
+    int64_t cap_pairs, cap_query_bytes, cap_subject_bytes;
+    int64_t npairs;            /* producer sets it before submit; collect returns it */
+    const int32_t* scores;     /* collect: npairs scores (pinned, valid until release) */
+    float kernel_ms;           /* collect: device time of this chunk */
+    int32_t slot;              /* internal */
+} anyseq_batch_chunk;
+int anyseq_batch_stream_open(anyseq_ctx* ctx, const anyseq_scoring* sc, int64_t cap_pairs,
+                             int64_t cap_query_bytes, int64_t cap_subject_bytes, int slots,
+                             anyseq_batch_stream** out);
+int anyseq_batch_stream_acquire(anyseq_batch_stream* st, anyseq_batch_chunk* chunk);
+int anyseq_batch_stream_submit(anyseq_batch_stream* st, const anyseq_batch_chunk* chunk);
+int anyseq_batch_stream_finish(anyseq_batch_stream* st);
+int anyseq_batch_stream_collect(anyseq_batch_stream* st, anyseq_batch_chunk* chunk);
+int anyseq_batch_stream_release(anyseq_batch_stream* st, const anyseq_batch_chunk* chunk);
+int anyseq_batch_stream_stats(anyseq_batch_stream* st, anyseq_result* totals, int64_t* h2d_bytes, int64_t* d2h_bytes);
+void anyseq_batch_stream_close(anyseq_batch_stream* st);
 
 /* Multi-GPU column-strip wavefront for one long pair (one process per GPU).
  * Rank r of `nranks` owns subject columns [col_begin, col_end).  Its left

@@ -426,3 +426,108 @@ def test_affine_traceback_vs_oracle(aligner, oracle, m, n):
             if mode == "global":
                 opt = oracle.textbook_affine("global", q, s, sa, di, gi, ge)
                 assert oracle.column_score_affine(r.aligned_query, r.aligned_subject, sa, di, gi, ge) == opt == r.score
+
+
+# --------------------------------------------------------------------------- streaming batches
+def _read_pairs(rng, npairs):
+    qs, ss = [], []
+    for p in range(npairs):
+        q = _rand(rng, int(rng.integers(20, 160)))
+        s = _rand(rng, int(rng.integers(100, 520)))
+        if len(s) > len(q):
+            o = int(rng.integers(0, len(s) - len(q) + 1)); s[o:o + len(q)] = q; s[o + len(q) // 3] = ACGT[p % 4]
+        qs.append(q); ss.append(s)
+    return qs, ss
+
+
+def test_host_batch_is_chunked_and_exact(aligner, oracle):
+    """anyseq_score_batch with host buffers runs as a pipeline of pinned chunks; tiny chunk limits force many
+    chunks (and ragged chunk boundaries) -- scores must not depend on the chunking"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(5)
+    qs, ss = _read_pairs(rng, 3000)
+    qd, qo = _pack(qs); sd, so = _pack(ss)
+    sch = A.affine_scoring_scheme(2, -1, -2, -1)
+    want, _ = aligner.score_batch("semiglobal", qd, qo, sd, so, sch)
+    for p in range(0, 3000, 97):
+        assert want[p] == oracle.score_affine("semiglobal", qs[p], ss[p], 2, -1, -2, -1)[0]
+    try:
+        for pairs, nbytes in [(7, 1 << 16), (1000, 1 << 16), (64, 1 << 20)]:
+            aligner.set_option("batch_chunk_pairs", pairs)
+            aligner.set_option("batch_chunk_bytes", nbytes)
+            got, res = aligner.score_batch("semiglobal", qd, qo, sd, so, sch)
+            assert (got == want).all()
+            assert res.kernel_launches >= 3000 // max(pairs, 1)       # several chunks really ran
+    finally:
+        aligner.set_option("batch_chunk_pairs", 1 << 18)
+        aligner.set_option("batch_chunk_bytes", 64 << 20)
+
+
+def test_batch_stream_producer_consumer(aligner, oracle):
+    """the stream ABI itself: a producer thread fills pinned chunks while this thread collects"""
+    import threading
+    import anyseq_b200 as A
+    rng = np.random.default_rng(6)
+    qs, ss = _read_pairs(rng, 1200)
+    sch = A.linear_scoring_scheme(2, -1, -1)
+    st = aligner.batch_stream("global", sch, cap_pairs=100, cap_query_bytes=1 << 15, cap_subject_bytes=1 << 16, slots=2)
+    errors = []
+
+    def produce():
+        try:
+            p = 0
+            while p < len(qs):
+                c, q, qo, s, so = st.acquire()
+                k = nq = ns = 0
+                qo[0] = so[0] = 0
+                while p < len(qs) and k < c.cap_pairs and nq + len(qs[p]) <= c.cap_query_bytes and \
+                        ns + len(ss[p]) <= c.cap_subject_bytes:
+                    q[nq:nq + len(qs[p])] = qs[p]; s[ns:ns + len(ss[p])] = ss[p]
+                    nq += len(qs[p]); ns += len(ss[p]); k += 1; p += 1
+                    qo[k] = nq; so[k] = ns
+                st.submit(c, k)
+        except Exception as e:     # noqa: BLE001
+            errors.append(e)
+        st.finish()
+
+    t = threading.Thread(target=produce)
+    t.start()
+    got = []
+    while True:
+        r = st.collect()
+        if r is None:
+            break
+        c, scores = r
+        got.extend(int(x) for x in scores)
+        st.release(c)
+    t.join()
+    info = st.stats()
+    st.close()
+    assert not errors, errors
+    assert len(got) == 1200 and info["h2d_bytes"] > sum(map(len, qs)) and info["d2h_bytes"] == 4 * 1200
+    for p in range(0, 1200, 13):
+        assert got[p] == oracle.score_linear("global", qs[p], ss[p])[0], p
+
+
+def test_cli_batch_mode(oracle, tmp_path):
+    """align --batch: FASTQ reads x multi-line FASTA windows, streamed through the batch path"""
+    from anyseq_b200 import build
+    build.build()
+    rng = np.random.default_rng(8)
+    qs, ss = _read_pairs(rng, 257)
+    fq, fa, out = tmp_path / "reads.fq", tmp_path / "windows.fa", tmp_path / "scores.tsv"
+    with open(fq, "w") as f:
+        for k, q in enumerate(qs):
+            f.write(f"@r{k}\n{bytes(q).decode()}\n+\n{'I' * len(q)}\n")
+    with open(fa, "w") as f:
+        for k, s in enumerate(ss):
+            t = bytes(s).decode()
+            f.write(f">w{k}\n" + "\n".join(t[i:i + 60] for i in range(0, len(t), 60)) + "\n")
+    r = subprocess.run([build.CLI, "-o", str(out), "--mode", "semiglobal", "--gap-init", "-2", "-b", str(fq), str(fa)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = open(out).read().strip().splitlines()
+    assert len(lines) == 257
+    for k in range(0, 257, 8):
+        idx, sc = lines[k].split("\t")
+        assert int(idx) == k + 1 and int(sc) == oracle.score_affine("semiglobal", qs[k], ss[k], 2, -1, -2, -1)[0]

@@ -80,6 +80,71 @@ print("rank", rank, "ok", res.score)
 '''
 
 
+_WORKER_TOKENS = r'''
+import os, sys, time, random
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch
+import torch.distributed as dist
+from anyseq_b200.multigpu import RunTokens, shard_batch, pair_ranges
+from oracle import oracle as O
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# --- run tokens: rank r may start run k only after rank r+1 has finished run k - depth
+depth, runs = 2, 9
+tok = RunTokens(dist, dist.new_group(backend="gloo"), rank, world, depth)
+log = []
+random.seed(rank)
+for k in range(runs):
+    tok.acquire(k)
+    log.append(("start", k, time.monotonic()))
+    time.sleep(random.random() * 0.02 * (3 if rank == world - 1 else 1))   # the last rank is the slow one
+    log.append(("end", k, time.monotonic()))
+    tok.release(k)
+tok.drain(runs)
+logs = [None] * world
+dist.all_gather_object(logs, log)
+for r in range(world - 1):
+    start = {k: t for (e, k, t) in logs[r] if e == "start"}
+    end_next = {k: t for (e, k, t) in logs[r + 1] if e == "end"}
+    for k in range(depth, runs):
+        assert end_next[k - depth] <= start[k] + 1e-4, (r, k)
+# --- batch sharding: contiguous ranges, scores gathered in pair order
+rng = np.random.default_rng(3)
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+qs = [ACGT[rng.integers(0, 4, int(rng.integers(1, 40)))] for _ in range(23)]
+ss = [ACGT[rng.integers(0, 4, int(rng.integers(1, 90)))] for _ in range(23)]
+qo = np.concatenate([[0], np.cumsum([len(x) for x in qs])]); so = np.concatenate([[0], np.cumsum([len(x) for x in ss])])
+qd, sd = np.concatenate(qs), np.concatenate(ss)
+p0, p1, (qa, qb), (sa, sb), lqo, lso = shard_batch(qo, so, rank, world)
+assert (p0, p1) == pair_ranges(23, world)[rank] and lqo[0] == 0 and lso[0] == 0
+lq, ls = qd[qa:qb], sd[sa:sb]
+local = np.array([O.score_linear("global", lq[lqo[i]:lqo[i + 1]], ls[lso[i]:lso[i + 1]])[0] for i in range(p1 - p0)], dtype=np.int32)
+parts = [None] * world
+dist.all_gather_object(parts, local.tobytes())
+allsc = np.concatenate([np.frombuffer(b, dtype=np.int32) for b in parts])
+want = [O.score_linear("global", qs[i], ss[i])[0] for i in range(23)]
+assert allsc.tolist() == want
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_run_tokens_and_batch_sharding_gloo():
+    """N > 1 host logic on CPU (gloo, world_size 2): neighbour run tokens that let consecutive alignments
+    overlap across ranks without overwriting an inbox in use, and contiguous sharding of a batch of pairs"""
+    with tempfile.TemporaryDirectory() as td:
+        w = os.path.join(td, "worker.py")
+        open(w, "w").write(_WORKER_TOKENS)
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29519", w, ROOT],
+                           capture_output=True, text=True, env=env, timeout=240)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("ok") == 2
+
+
 def test_multi_rank_combine_gloo():
     """N > 1 host path: per-rank partial results gathered with torch.distributed (gloo,
     world_size 2) and combined exactly like a single-GPU semiglobal run"""
