@@ -53,6 +53,7 @@ class AlignmentResult:
     kernel_launches: int
     aligned_query: bytes | None = None
     aligned_subject: bytes | None = None
+    start: tuple | None = None       # full-matrix traceback: get_alignment_start()
 
     def cigar(self) -> str:
         if self.aligned_query is None:
@@ -144,6 +145,22 @@ class Aligner:
                                            capi._ptr(oq), capi._ptr(os_), C.byref(res)))
         return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches,
                                oq[:n].tobytes(), os_[:n].tobytes())
+
+    # -- traceback_full(): src/align.impala:190-216 ------------------------
+    def align_full(self, mode, query, subject, scoring: ScoringScheme = REFERENCE_SCORING) -> AlignmentResult:
+        """full predecessor matrix + one walk from get_score_pos(): exact semiglobal / local alignments;
+        m*n/2 bytes of HBM (AnyseqError ANYSEQ_ERR_UNSUPPORTED when that does not fit)"""
+        q, s = as_u8(query), as_u8(subject)
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        n = len(q) + len(s)
+        oq = np.zeros(max(n, 1), dtype=np.uint8)
+        os_ = np.zeros(max(n, 1), dtype=np.uint8)
+        start = (C.c_int32 * 2)()
+        self._check(self._lib.anyseq_align_full(self._ctx, C.byref(sc), capi._ptr(q), len(q), capi._ptr(s), len(s),
+                                                capi._ptr(oq), capi._ptr(os_), C.byref(res), start))
+        return AlignmentResult(res.score, res.end_i, res.end_j, res.kernel_ms, res.kernel_launches,
+                               oq[:n].tobytes(), os_[:n].tobytes(), (int(start[0]), int(start[1])))
 
     def last_splits(self):
         """split rows of the last align() (slot -1 first), src/traceback_lintime.impala:9-42"""

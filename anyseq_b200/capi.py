@@ -22,6 +22,8 @@ MODES = {"global": GLOBAL, "semiglobal": SEMIGLOBAL, "local": LOCAL}
 EXPORTED_SYMBOLS = [
     "global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
     "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
+    "construct_global_alignment_fulltb", "construct_semiglobal_alignment_fulltb", "construct_local_alignment_fulltb",
+    "anyseq_align_full",
     "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
     "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_last_split_types", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
@@ -83,7 +85,9 @@ def load_library(path: str | None = None):
         f = getattr(L, name)
         f.restype = C.c_int64
         f.argtypes = [vp, C.c_int, vp, C.c_int]
-    for name in ("construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment"):
+    for name in ("construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
+                 "construct_global_alignment_fulltb", "construct_semiglobal_alignment_fulltb",
+                 "construct_local_alignment_fulltb"):
         f = getattr(L, name)
         f.restype = C.c_int64
         f.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
@@ -103,6 +107,9 @@ def load_library(path: str | None = None):
     L.anyseq_score_device.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.POINTER(Result)]
     L.anyseq_align.restype = C.c_int
     L.anyseq_align.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, vp, vp, C.POINTER(Result)]
+    L.anyseq_align_full.restype = C.c_int
+    L.anyseq_align_full.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, vp, vp, C.POINTER(Result),
+                                    C.POINTER(C.c_int32)]
     L.anyseq_last_splits.restype = C.c_int
     L.anyseq_last_splits.argtypes = [vp, C.POINTER(C.c_int32), C.c_int]
     L.anyseq_last_split_types.restype = C.c_int

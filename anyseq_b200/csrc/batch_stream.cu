@@ -58,6 +58,24 @@ public:
     BatchStream(Engine* eng, const anyseq_scoring& sc) : eng_(eng), sc_(sc) {}
     ~BatchStream() { destroy(); }
 
+    // reuse of an idle stream (every slot free) for another batch: pinned allocations are expensive
+    bool reusable(int64_t cap_pairs, int64_t cap_q, int64_t cap_s) const
+    {
+        return !slots_.empty() && !failed_ && cap_pairs <= cap_pairs_ && cap_q <= cap_q_ && cap_s <= cap_s_;
+    }
+    void restart(const anyseq_scoring& sc)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        sc_ = sc;
+        order_.clear();
+        for (BatchSlot& s : slots_) s.state = BatchSlot::kFree;
+        finished_ = false;
+        next_fill_ = 0;
+        kernel_ms_ = 0.f;
+        launches_ = 0;
+        h2d_bytes_ = d2h_bytes_ = 0;
+    }
+
     int init(int64_t cap_pairs, int64_t cap_q, int64_t cap_s, int nslots)
     {
         cap_pairs_ = std::max<int64_t>(1, cap_pairs);
@@ -291,9 +309,24 @@ int Engine::score_batch_host(const anyseq_scoring& sc, const char* q, const int6
     const int64_t cap_s = std::max<int64_t>(max_pair_s, (int64_t)(target * (1.0 - fq)) + 1) + 64;
     const int64_t cap_pairs = std::min<int64_t>(npairs, std::max<int64_t>(1, (int64_t)tune.batch_chunk_pairs));
 
-    BatchStream st(this, sc);
-    rc = st.init(cap_pairs, cap_q, cap_s, 3);
-    if (rc) return rc;
+    // one cached stream per engine: its pinned + device slots survive between calls
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    BatchStream* cached = static_cast<BatchStream*>(host_batch_stream_);
+    if (cached && !cached->reusable(cap_pairs, cap_q, cap_s)) {
+        delete cached;
+        cached = nullptr;
+        host_batch_stream_ = nullptr;
+    }
+    if (!cached) {
+        cached = new BatchStream(this, sc);
+        rc = cached->init(std::max<int64_t>(cap_pairs, std::min<int64_t>(tune.batch_chunk_pairs, 1 << 18)), cap_q, cap_s, 3);
+        if (rc) { delete cached; return rc; }
+        host_batch_stream_ = cached;
+    }
+    cached->restart(sc);
+    BatchStream& st = *cached;
+    // chunk limits of THIS call (the cached stream's slots may be larger)
+    const int64_t chunk_pairs = cap_pairs, chunk_q = cap_q, chunk_s = cap_s;
     const int copy_threads = std::max(1, std::min(tune.batch_copy_threads, (int)std::thread::hardware_concurrency()));
     int producer_rc = ANYSEQ_OK;
     std::thread producer([&] {
@@ -302,7 +335,7 @@ int Engine::score_batch_host(const anyseq_scoring& sc, const char* q, const int6
             anyseq_batch_chunk c;
             if ((producer_rc = st.acquire(&c)) != ANYSEQ_OK) break;
             int64_t e = p;
-            while (e < npairs && e - p < cap_pairs && qoff[e + 1] - qoff[p] <= cap_q && soff[e + 1] - soff[p] <= cap_s) ++e;
+            while (e < npairs && e - p < chunk_pairs && qoff[e + 1] - qoff[p] <= chunk_q && soff[e + 1] - soff[p] <= chunk_s) ++e;
             const int64_t np = e - p;
             for (int64_t i = 0; i <= np; ++i) { c.q_off[i] = qoff[p + i] - qoff[p]; c.s_off[i] = soff[p + i] - soff[p]; }
             parallel_copy(c.queries, q + qoff[p], (size_t)(qoff[e] - qoff[p]), copy_threads);
@@ -326,11 +359,21 @@ int Engine::score_batch_host(const anyseq_scoring& sc, const char* q, const int6
     }
     if (crc != ANYSEQ_EOF) st.fail();
     producer.join();
+    if (crc != ANYSEQ_EOF || producer_rc != ANYSEQ_OK) {     // do not reuse a stream that failed
+        delete cached;
+        host_batch_stream_ = nullptr;
+    }
     if (crc != ANYSEQ_EOF) return crc;
     if (producer_rc != ANYSEQ_OK) return producer_rc;
     if (done != npairs) { set_last_error("batch stream lost pairs"); return ANYSEQ_ERR_BAD_ARG; }
     st.stats(out, nullptr, nullptr);
     return ANYSEQ_OK;
+}
+
+void Engine::drop_host_batch_stream()
+{
+    delete static_cast<BatchStream*>(host_batch_stream_);
+    host_batch_stream_ = nullptr;
 }
 
 }  // namespace anyseq

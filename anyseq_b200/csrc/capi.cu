@@ -101,6 +101,16 @@ int anyseq_align(anyseq_ctx* ctx, const anyseq_scoring* sc, const char* query, i
     return ctx->eng.align_host(*sc, query, lenq, subject, lens, alQuery, alSubject, out);
 }
 
+int anyseq_align_full(anyseq_ctx* ctx, const anyseq_scoring* sc, const char* query, int lenq,
+                      const char* subject, int lens, char* alQuery, char* alSubject, anyseq_result* out, int32_t* start)
+{
+    if (!ctx || !sc || !out || !alQuery || !alSubject) return ANYSEQ_ERR_BAD_ARG;
+    int st[2] = {0, 0};
+    const int rc = ctx->eng.align_full_host(*sc, query, lenq, subject, lens, alQuery, alSubject, out, st);
+    if (start) { start[0] = st[0]; start[1] = st[1]; }
+    return rc;
+}
+
 int anyseq_last_splits(anyseq_ctx* ctx, int32_t* out, int cap)
 {
     if (!ctx) return ANYSEQ_ERR_BAD_ARG;
@@ -318,6 +328,23 @@ static score_t legacy_align(int mode, const char* q, int lenq, const char* s, in
     if (mode == ANYSEQ_SEMIGLOBAL) return 0;
     return (score_t)anyseq::kScoreMin;
 }
+
+// traceback_full exports (src/export.impala:38,94,151): the scoring object has been relaxed there, so these
+// return the real score
+static score_t legacy_align_full(int mode, const char* q, int lenq, const char* s, int lens, char* alq, char* als)
+{
+    anyseq_scoring sc = {mode, 2, -1, 0, -1};
+    anyseq_result res;
+    int rc = anyseq_align_full(default_ctx(), &sc, q, lenq, s, lens, alq, als, &res, nullptr);
+    if (rc) {
+        std::fprintf(stderr, "anyseq_b200: full-matrix alignment failed (%d): %s\n", rc, anyseq_last_error());
+        std::abort();
+    }
+    return (score_t)res.score;
+}
+score_t construct_global_alignment_fulltb(const char* q, int lenq, const char* s, int lens, char* alq, char* als) { return legacy_align_full(ANYSEQ_GLOBAL, q, lenq, s, lens, alq, als); }
+score_t construct_semiglobal_alignment_fulltb(const char* q, int lenq, const char* s, int lens, char* alq, char* als) { return legacy_align_full(ANYSEQ_SEMIGLOBAL, q, lenq, s, lens, alq, als); }
+score_t construct_local_alignment_fulltb(const char* q, int lenq, const char* s, int lens, char* alq, char* als) { return legacy_align_full(ANYSEQ_LOCAL, q, lenq, s, lens, alq, als); }
 
 score_t global_alignment_score(const char* q, int lenq, const char* s, int lens) { return legacy_score(ANYSEQ_GLOBAL, q, lenq, s, lens); }
 score_t semiglobal_alignment_score(const char* q, int lenq, const char* s, int lens) { return legacy_score(ANYSEQ_SEMIGLOBAL, q, lenq, s, lens); }

@@ -58,6 +58,7 @@ struct Job {
     int* best;               // local mode: running maximum (atomicMax)
     unsigned long long* blockmax;   // local end-cell tracking: per 1024 x 1024 reference block (value, -position) keys
     int nbj;                 // number of 1024-column blocks (row pitch of blockmax)
+    int2* edges;             // optional [nstrips][h]: (H, E) of every strip's last column, kept for the full-matrix traceback
     // multi-GPU chaining (null on a single GPU): strip 0 consumes the records
     // tagged in_tag from `in` (this rank's inbox, written by the previous rank
     // over NVLink); the last strip mirrors its right edge into `out` (the next

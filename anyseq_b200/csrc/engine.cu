@@ -292,7 +292,8 @@ void Engine::destroy()
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
                             &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
-                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_, &blockmax_};
+                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_, &blockmax_, &edges_};
+    drop_host_batch_stream();
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -497,13 +498,13 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
     const bool local = sc.mode == ANYSEQ_LOCAL;
     // the end cell of a local alignment needs the whole matrix in one job (reference block grid)
-    const bool track = local && tune.local_end_cell && !inbox && !next_inbox && col_begin == 0 && col_end == n_total;
+    const bool track = local && (tune.local_end_cell || force_track_) && !inbox && !next_inbox && col_begin == 0 && col_end == n_total;
     struct TrackScope { bool& t; ~TrackScope() { t = false; } } track_scope{track_};
     track_ = track;
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     rc = analyse_alphabet(d_q, m, d_s_slice, w);
     if (rc) return rc;
-    const int K = pick_K(w);
+    const int K = want_edges_ ? 4 : pick_K(w);     // edge columns are wanted per 128-column block
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
     const int resident = resident_warps(K, local, affine, nstrips);
@@ -539,6 +540,10 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
         ANYSEQ_CUDA_CHECK(cudaMemsetAsync(blockmax_.ptr, 0, bytes, stream_));
         J.blockmax = blockmax_.as<unsigned long long>();
         J.nbj = nbj;
+    }
+    if (want_edges_) {
+        if (edges_.ensure(sizeof(int2) * (size_t)nstrips * (size_t)m)) return ANYSEQ_ERR_NO_DEVICE;
+        J.edges = edges_.as<int2>();
     }
     // the tag of a run is agreed without communication: both ends count their uses of the inbox
     if (inbox) { J.in = inbox->records; J.in_tag = 0x40000000 + (++inbox->uses_in & 0xffffff); }

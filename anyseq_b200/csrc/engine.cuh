@@ -81,6 +81,9 @@ public:
                    char* alq, char* als, anyseq_result* out);
     int align_host_affine(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                           char* alq, char* als, anyseq_result* out);
+    // full-matrix traceback (traceback_full.cu); start2 = get_alignment_start()
+    int align_full_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                        char* alq, char* als, anyseq_result* out, int* start2);
     int score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, const int64_t* d_qoff,
                            const uint8_t* d_s, const int64_t* d_soff, int64_t npairs,
                            int32_t* d_scores, anyseq_result* out);
@@ -97,11 +100,13 @@ public:
     Tuning tune;
     const std::vector<int>& last_splits() const { return last_splits_; }
     const std::vector<int>& last_types() const { return last_types_; }
+    const int* last_start() const { return last_start_; }
     int device = -1;
     int sm_count = 0;
     char name[64] = {0};
     int resident_warps(int K, bool local, bool affine, long long nstrips = 1LL << 40);
     cudaStream_t stream() const { return stream_; }
+    void drop_host_batch_stream();       // batch_stream.cu: the cached pipeline of score_batch_host
 
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
@@ -118,12 +123,17 @@ private:
     DeviceBuffer col2_;               // second column-record set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
+    DeviceBuffer edges_;         // full-matrix traceback: right edge column (H, E) of every 128-column strip
     DeviceBuffer blockmax_;      // local end-cell tracking: one key per 1024 x 1024 reference block
     int* h_misc_ = nullptr;           // pinned mirror of misc_
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
     std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)
     int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)
     bool use_mask_ = false;
+    void* host_batch_stream_ = nullptr;  // BatchStream* reused by score_batch_host
+    bool want_edges_ = false;    // the running score call keeps the strips' edge columns (K = 4)
+    bool force_track_ = false;   // ... and tracks the local end cell whatever the option says
+    int last_start_[2] = {0, 0}; // get_alignment_start() of the last full-matrix traceback
     bool track_ = false;         // the running score call tracks the local end cell
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
     std::recursive_mutex mu_;

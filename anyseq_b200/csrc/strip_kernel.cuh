@@ -496,6 +496,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             const int2 v = sm.out[r & 63];
             st_record(colout + r, make_int4(v.x - go, my_tag, v.y, my_tag));
             if (mirror) st_record(J.out + i0 + r, make_int4(v.x - go, J.out_tag, v.y, J.out_tag));
+            if (J.edges) __stcg(J.edges + (size_t)strip * J.h + i0 + r, make_int2(v.x - go, v.y));
         }
     };
     // MASK: tile mask of row group g = sum over its rows of (spread mask of the row's code) << r

@@ -53,6 +53,18 @@ score_t construct_semiglobal_alignment(const char* query, int lenq, const char* 
 score_t construct_local_alignment(const char* query, int lenq, const char* subject, int lens,
                                   char* alQuery, char* alSubject);
 
+/* The full-matrix variants the Impala side also exports (src/export.impala:38,94,151; not declared in
+ * src/import.h): traceback_full, src/align.impala:190-216 -- the whole predecessor matrix and ONE walk from
+ * get_score_pos(), i.e. the exact semiglobal / local alignments the linear-space path does not give.
+ * Same buffers and output layout; they return the real score (the scoring object is relaxed there).
+ * Memory is m*n/2 bytes of HBM: pairs up to roughly 400 k x 400 k on a 180 GB B200; abort()s beyond. */
+score_t construct_global_alignment_fulltb(const char* query, int lenq, const char* subject, int lens,
+                                          char* alQuery, char* alSubject);
+score_t construct_semiglobal_alignment_fulltb(const char* query, int lenq, const char* subject, int lens,
+                                              char* alQuery, char* alSubject);
+score_t construct_local_alignment_fulltb(const char* query, int lenq, const char* subject, int lens,
+                                         char* alQuery, char* alSubject);
+
 /* ---------------------------------------------------------------------------
  * 2. Parametrised surface.
  * ------------------------------------------------------------------------- */
@@ -148,6 +160,13 @@ int anyseq_last_splits(anyseq_ctx* ctx, int32_t* out, int cap);
  * gap runs through it), same indexing as anyseq_last_splits; empty after a
  * linear-gap traceback. */
 int anyseq_last_split_types(anyseq_ctx* ctx, int32_t* out, int cap);
+
+/* traceback_full() with a parametrised scheme (Gotoh: build-defined, parity unpinned).  start[2] (optional)
+ * receives get_alignment_start() = the cell after which the walk stopped; out->end_i/end_j the cell it
+ * began at (get_score_pos()).  ANYSEQ_ERR_UNSUPPORTED when the predecessor matrix does not fit. */
+int anyseq_align_full(anyseq_ctx* ctx, const anyseq_scoring* sc,
+                      const char* query, int lenq, const char* subject, int lens,
+                      char* alQuery, char* alSubject, anyseq_result* out, int32_t* start);
 
 /* Derived view of an alignment pair: CIGAR string (=/X/I/D run-length, I = gap
  * in the query ('_' in alQuery), D = gap in the subject), skipping blank

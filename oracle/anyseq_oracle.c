@@ -894,6 +894,122 @@ int32_t oracle_traceback_lintime_affine(int mode,
     return ORACLE_SCORE_MIN;
 }
 
+/* ======================================================================
+ * traceback_full: src/align.impala:190-216 -- the whole predecessor matrix
+ * (full_predecessors, src/predecessors.impala:11-34: border row/column from
+ * init_predc_rows/cols), relaxed with the scheme's relax (the order of the
+ * relaxation does not influence the predecessors), then ONE walk
+ * (traceback_offset, src/traceback.impala:47-80) from scoring.get_score_pos()
+ * (src/scoring.impala:33-34, 46-64, 103-110).  Unlike traceback_lintime the
+ * scoring object HAS been relaxed, so the returned value is the real score.
+ * Element (i,j), i,j >= -1, lives at (i+1)*(n+1) + (j+1).
+ * ====================================================================== */
+int32_t oracle_traceback_full(int mode, const uint8_t* q, int m, const uint8_t* s, int n,
+                              int same, int diff, int gap, uint8_t* out_q, uint8_t* out_s,
+                              int32_t* start_out, int threads)
+{
+    const int local = mode == ORACLE_LOCAL;
+    for (int k = 0; k < m + n; ++k) { out_q[k] = EMPTY_SYM; out_s[k] = EMPTY_SYM; }   /* src/traceback.impala:20-23 */
+    const oracle_result r = oracle_score_linear(mode, q, m, s, n, same, diff, gap, threads, 0, 0);
+    if (m <= 0 || n <= 0) { if (start_out) { start_out[0] = 0; start_out[1] = 0; } return r.score; }
+    const size_t pitch = (size_t)n + 1;
+    uint8_t* pred = (uint8_t*)malloc(((size_t)m + 1) * pitch);
+    #define PF(i, j) pred[(size_t)((i) + 1) * pitch + (size_t)((j) + 1)]
+    for (int i = -1; i < m; ++i) PF(i, -1) = init_predc_rows(mode, i);
+    for (int j = 0; j < n; ++j) PF(-1, j) = init_predc_cols(mode, j);
+    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    for (int j = 0; j < n; ++j) row[j] = init_score(mode, gap, j);
+    for (int i = 0; i < m; ++i) {
+        int32_t no_gap = init_score(mode, gap, i - 1);
+        int32_t gap_q = init_score(mode, gap, i);
+        for (int j = 0; j < n; ++j) {
+            const int32_t gap_s = row[j];
+            uint8_t p;
+            const int32_t sc = relax_cell(local, q[i], s[j], no_gap, gap_q, gap_s, same, diff, gap, &p);
+            PF(i, j) = p;
+            no_gap = gap_s; gap_q = sc; row[j] = sc;
+        }
+    }
+    int i = r.pos_i, j = r.pos_j;
+    uint8_t p = PF(i, j);
+    while (p != PRED_NONE) {
+        uint8_t sq = GAP_SYM, ss = GAP_SYM;
+        const int out_pos = i + j + 1;
+        if (p == PRED_NO_GAP || p == PRED_GAP_S) { sq = q[i]; --i; }
+        if (p == PRED_NO_GAP || p == PRED_GAP_Q) { ss = s[j]; --j; }
+        out_q[out_pos] = sq; out_s[out_pos] = ss;
+        p = PF(i, j);
+    }
+    #undef PF
+    if (start_out) { start_out[0] = i + 1; start_out[1] = j + 1; }      /* get_alignment_start */
+    free(row); free(pred);
+    return r.score;
+}
+
+/* Gotoh full-matrix traceback, BUILD-DEFINED like the other affine entry points
+ * (*** parity unpinned vs the reference ***): 4 predecessor bits per cell and the
+ * 3-state walk of the final pass of oracle_traceback_lintime_affine, over the whole
+ * matrix, started in state H at the end cell of oracle_score_affine.  gi == 0
+ * reproduces oracle_traceback_full. */
+int32_t oracle_traceback_full_affine(int mode, const uint8_t* q, int m, const uint8_t* s, int n,
+                                     int same, int diff, int gi, int ge, uint8_t* out_q, uint8_t* out_s,
+                                     int32_t* start_out, int threads)
+{
+    const int glob = mode == ORACLE_GLOBAL, loc = mode == ORACLE_LOCAL;
+    const int go = gi + ge;
+    for (int k = 0; k < m + n; ++k) { out_q[k] = EMPTY_SYM; out_s[k] = EMPTY_SYM; }
+    const oracle_result r = oracle_score_affine(mode, q, m, s, n, same, diff, gi, ge, threads, 0, 0);
+    if (m <= 0 || n <= 0) { if (start_out) { start_out[0] = 0; start_out[1] = 0; } return r.score; }
+    uint8_t* pred = (uint8_t*)malloc((size_t)m * (size_t)n);
+    int32_t* Hrow = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* Frow = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    for (int j = 0; j < n; ++j) { Hrow[j] = glob ? gi + (j + 1) * ge : 0; Frow[j] = NEG_INF; }
+    int32_t diag0 = 0;
+    for (int i = 0; i < m; ++i) {
+        int32_t hleft = glob ? gi + (i + 1) * ge : 0;
+        int32_t e = NEG_INF, diag = diag0;
+        diag0 = hleft;
+        for (int j = 0; j < n; ++j) {
+            const int32_t up = Hrow[j];
+            int eext = 0, fext = 0;
+            int32_t eo = hleft + go;
+            if (e + ge > eo) { eo = e + ge; eext = 1; }
+            e = eo;
+            int32_t fo = up + go;
+            if (Frow[j] + ge > fo) { fo = Frow[j] + ge; fext = 1; }
+            int32_t sc = diag + (q[i] == s[j] ? same : diff);
+            int src = PRED_NO_GAP;
+            if (e > sc) { sc = e; src = PRED_GAP_Q; }
+            if (fo > sc) { sc = fo; src = PRED_GAP_S; }
+            if (loc && 0 > sc) { sc = 0; src = PRED_NONE; }
+            pred[(size_t)i * n + j] = (uint8_t)(src | (eext << 2) | (fext << 3));
+            diag = up; hleft = sc; Hrow[j] = sc; Frow[j] = fo;
+        }
+    }
+    int i = r.pos_i, j = r.pos_j, state = 0;
+    for (;;) {
+        if (i < 0 && j < 0) break;
+        if (i < 0) { if (!glob) break; out_q[i + j + 1] = GAP_SYM; out_s[i + j + 1] = s[j]; --j; continue; }
+        if (j < 0) { if (!glob) break; out_q[i + j + 1] = q[i]; out_s[i + j + 1] = GAP_SYM; --i; continue; }
+        const uint8_t p = pred[(size_t)i * n + j];
+        if (state == 0) {
+            const int src = p & 3;
+            if (src == PRED_NONE) break;
+            if (src == PRED_NO_GAP) { out_q[i + j + 1] = q[i]; out_s[i + j + 1] = s[j]; --i; --j; }
+            else state = (src == PRED_GAP_Q) ? 1 : 2;
+        } else if (state == 1) {
+            out_q[i + j + 1] = GAP_SYM; out_s[i + j + 1] = s[j];
+            state = ((p >> 2) & 1) ? 1 : 0; --j;
+        } else {
+            out_q[i + j + 1] = q[i]; out_s[i + j + 1] = GAP_SYM;
+            state = ((p >> 3) & 1) ? 2 : 0; --i;
+        }
+    }
+    if (start_out) { start_out[0] = i + 1; start_out[1] = j + 1; }
+    free(pred); free(Hrow); free(Frow);
+    return r.score;
+}
+
 /* affine column score of an emitted alignment (test helper): gap runs cost gi + L*ge */
 int64_t oracle_alignment_column_score_affine(const uint8_t* aq, const uint8_t* as, int len,
                                              int same, int diff, int gi, int ge)

@@ -99,6 +99,17 @@ int32_t oracle_traceback_lintime_affine(int mode,
 int64_t oracle_alignment_column_score_affine(const uint8_t* aq, const uint8_t* as, int len,
                                              int same, int diff, int gap_init, int gap_extend);
 
+/* traceback_full(): src/align.impala:190-216 -- full predecessor matrix (m*n bytes here: small cases
+ * only) + one walk from get_score_pos(); returns the REAL score (the scoring object was relaxed).
+ * start_out[2] = get_alignment_start() = (i+1, j+1) where the walk stopped. */
+int32_t oracle_traceback_full(int mode, const uint8_t* q, int m, const uint8_t* s, int n,
+                              int same, int diff, int gap, uint8_t* out_q, uint8_t* out_s,
+                              int32_t* start_out, int threads);
+/* Gotoh variant, BUILD-DEFINED (*** parity unpinned vs the reference ***) */
+int32_t oracle_traceback_full_affine(int mode, const uint8_t* q, int m, const uint8_t* s, int n,
+                                     int same, int diff, int gap_init, int gap_extend,
+                                     uint8_t* out_q, uint8_t* out_s, int32_t* start_out, int threads);
+
 /* reduce_max(): src/utils.impala:30-49 -> src/iteration_cpu.impala:205-250.
  * vec points at logical index 0 (index -1 must be addressable when offset=-1) */
 void oracle_reduce_max(const int32_t* vec, int offset, int length,

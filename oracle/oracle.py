@@ -62,6 +62,12 @@ def lib():
     L.oracle_traceback_lintime_affine.restype = C.c_int32
     L.oracle_traceback_lintime_affine.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                   u8p, u8p, i32p, i32p, C.c_int]
+    L.oracle_traceback_full.restype = C.c_int32
+    L.oracle_traceback_full.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        u8p, u8p, i32p, C.c_int]
+    L.oracle_traceback_full_affine.restype = C.c_int32
+    L.oracle_traceback_full_affine.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               u8p, u8p, i32p, C.c_int]
     L.oracle_alignment_column_score_affine.restype = C.c_int64
     L.oracle_alignment_column_score_affine.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.oracle_reduce_max.restype = None
@@ -151,6 +157,24 @@ def traceback_lintime_affine(mode, q, s, same=2, diff=-1, gap_init=-2, gap_exten
                                                 _ptr(oq), _ptr(os_), splits.ctypes.data_as(i32p),
                                                 types.ctypes.data_as(i32p), threads)
     return ret, oq[:m + n].tobytes(), os_[:m + n].tobytes(), splits, types
+
+
+def traceback_full(mode, q, s, same=2, diff=-1, gap_init=0, gap_extend=-1, threads=4):
+    """traceback_full of the reference (gap_init == 0) or the build-defined Gotoh variant.
+    Returns (score, aligned_q, aligned_s, (start_i, start_j))."""
+    q, s = _u8(q), _u8(s)
+    m, n = len(q), len(s)
+    oq = np.zeros(max(m + n, 1), dtype=np.uint8)
+    os_ = np.zeros(max(m + n, 1), dtype=np.uint8)
+    start = np.zeros(2, dtype=np.int32)
+    sp = start.ctypes.data_as(C.POINTER(C.c_int32))
+    if gap_init == 0:
+        ret = lib().oracle_traceback_full(_mode(mode), _ptr(q), m, _ptr(s), n, same, diff, gap_extend,
+                                          _ptr(oq), _ptr(os_), sp, threads)
+    else:
+        ret = lib().oracle_traceback_full_affine(_mode(mode), _ptr(q), m, _ptr(s), n, same, diff, gap_init, gap_extend,
+                                                 _ptr(oq), _ptr(os_), sp, threads)
+    return ret, oq[:m + n].tobytes(), os_[:m + n].tobytes(), (int(start[0]), int(start[1]))
 
 
 def column_score_affine(aq: bytes, as_: bytes, same=2, diff=-1, gap_init=-2, gap_extend=-1) -> int:

@@ -62,7 +62,7 @@ def main():
                    np.frombuffer(b"ACGTNNacgt\rACGGTacgtnnACGT" * 8, dtype=np.uint8)))
     for name, qq, ss in inputs:
         c = {"name": name, "q": bytes(qq).decode("latin-1"), "s": bytes(ss).decode("latin-1"), "linear": {}, "affine": {},
-             "traceback": {}}
+             "traceback": {}, "traceback_full": {}}
         for mode in ("global", "semiglobal", "local"):
             for key, (sa, di, ga) in {"2,-1,-1": (2, -1, -1), "3,-2,-4": (3, -2, -4)}.items():
                 sc = O.score_linear(mode, qq, ss, sa, di, ga)
@@ -77,6 +77,15 @@ def main():
                                     "column_score": O.column_score(aq, as_),
                                     "aq": aq.decode("latin-1") if len(aq) <= 2000 else None,
                                     "as": as_.decode("latin-1") if len(as_) <= 2000 else None}
+            # traceback_full (src/align.impala:190-216); "affine" = build-defined Gotoh variant (2,-1,-2,-1)
+            sc, aq, as_, st = O.traceback_full(mode, qq, ss)
+            assert sc == O.score_linear(mode, qq, ss)[0]
+            sca, aqa, asa, sta = O.traceback_full(mode, qq, ss, 2, -1, -2, -1)
+            assert sca == O.score_affine(mode, qq, ss)[0]
+            c["traceback_full"][mode] = {"score": sc, "sha": sha(aq, as_), "start": list(st),
+                                         "column_score": O.column_score(aq, as_),
+                                         "affine": {"score": sca, "sha": sha(aqa, asa), "start": list(sta),
+                                                    "column_score": O.column_score_affine(aqa, asa)}}
         cases.append(c)
     out = {"generator": "tests/golden/make_golden.py", "appendix_c": {
         "align -r": {"m": 861, "n": 914, "scores": [654, 659, 659], "fnv_q": "4de67cd69011a8a7", "fnv_s": "08f2452b0e6358ff",

@@ -531,3 +531,75 @@ def test_cli_batch_mode(oracle, tmp_path):
     for k in range(0, 257, 8):
         idx, sc = lines[k].split("\t")
         assert int(idx) == k + 1 and int(sc) == oracle.score_affine("semiglobal", qs[k], ss[k], 2, -1, -2, -1)[0]
+
+
+# --------------------------------------------------------------------------- full-matrix traceback
+def test_traceback_full_golden_and_legacy_symbols(aligner, golden):
+    import anyseq_b200 as A
+    L = A.capi.load_library()
+    for c in golden["cases"]:
+        q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
+        for mode in MODES:
+            t = c["traceback_full"][mode]
+            r = aligner.align_full(mode, q, s)
+            assert (r.score, list(r.start), _sha(r.aligned_query, r.aligned_subject)) == (t["score"], t["start"], t["sha"]), \
+                (c["name"], mode)
+            r = aligner.align_full(mode, q, s, A.affine_scoring_scheme(2, -1, -2, -1))
+            ta = t["affine"]
+            assert (r.score, list(r.start), _sha(r.aligned_query, r.aligned_subject)) == (ta["score"], ta["start"], ta["sha"]), \
+                (c["name"], mode, "affine")
+            # construct_*_alignment_fulltb (src/export.impala:38,94,151): same bytes, real score
+            qa, sa = A.capi.as_u8(q), A.capi.as_u8(s)
+            oq = np.zeros(len(qa) + len(sa), np.uint8); os_ = np.zeros(len(qa) + len(sa), np.uint8)
+            ret = getattr(L, f"construct_{mode}_alignment_fulltb")(A.capi._ptr(qa), len(qa), A.capi._ptr(sa), len(sa),
+                                                                   A.capi._ptr(oq), A.capi._ptr(os_))
+            assert ret == t["score"] and _sha(oq.tobytes(), os_.tobytes()) == t["sha"]
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 300), (300, 1), (127, 128), (200, 129), (129, 4100), (4100, 129), (2500, 3333),
+                                 (7000, 5000)])
+def test_traceback_full_vs_oracle(aligner, oracle, m, n):
+    import anyseq_b200 as A
+    rng = np.random.default_rng(m * 7 + n)
+    q = _rand(rng, m)
+    s = _related(rng, q, n) if min(m, n) > 50 else _rand(rng, n)
+    if min(m, n) > 400:                      # overlap layout: semiglobal and local differ from global
+        s = np.concatenate([_rand(rng, n - n // 2), q[: n // 2]])[:n]
+        s[rng.integers(0, n, n // 30)] = ACGT[0]
+    for mode in MODES:
+        for sch in (A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1), A.linear_scoring_scheme(3, -2, -4),
+                    A.affine_scoring_scheme(5, -4, -10, -1)):
+            r = aligner.align_full(mode, q, s, sch)
+            sc, aq, as_, st = oracle.traceback_full(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+            assert r.score == sc and r.start == st, (mode, sch)
+            assert (r.aligned_query, r.aligned_subject) == (aq, as_), (mode, sch)
+
+
+def test_traceback_full_large_and_refusal(aligner):
+    """30 k x 25 k (375 MB of predecessors): exact local / semiglobal alignments (column score == score);
+    a pair whose matrix cannot fit is refused, not silently truncated"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(3)
+    core = _rand(rng, 20000)
+    q = np.concatenate([_rand(rng, 5000), core, _rand(rng, 5000)])
+    s = np.concatenate([_rand(rng, 2000), _related(rng, core, 20000, sub=0.03), _rand(rng, 3000)])
+    for mode in ("local", "semiglobal", "global"):
+        for sch in (A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1)):
+            r = aligner.align_full(mode, q, s, sch)
+            assert r.score == aligner.score(mode, q, s, sch).score
+            aq, as_ = np.frombuffer(r.aligned_query, np.uint8), np.frombuffer(r.aligned_subject, np.uint8)
+            keep = ~((aq == 32) & (as_ == 32))
+            a, b = aq[keep], as_[keep]
+            gq, gs = a == 95, b == 95
+            sub = int((np.where(a == b, sch.same, sch.diff) * ~(gq | gs)).sum())
+            runs = int((gq[1:] & ~gq[:-1]).sum() + gq[0] + (gs[1:] & ~gs[:-1]).sum() + gs[0])
+            col = sub + sch.gap_extend * int(gq.sum() + gs.sum()) + sch.gap_init * runs
+            assert col == r.score, (mode, sch, col, r.score)
+            dq = bytes(a[~gq]); ds = bytes(b[~gs])
+            assert bytes(q)[r.start[0]:r.start[0] + len(dq)] == dq and bytes(s)[r.start[1]:r.start[1] + len(ds)] == ds
+            if mode == "local":
+                assert len(dq) > 15000          # the planted core is found
+    big = np.zeros(3_000_000, np.uint8) + 65
+    with pytest.raises(A.AnyseqError) as e:
+        aligner.align_full("global", big, big)
+    assert e.value.code == -4

@@ -149,6 +149,44 @@ def test_golden_fixtures(oracle, golden):
             assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == t["sha"]
 
 
+def test_traceback_full_properties_and_fixtures(oracle, golden):
+    """traceback_full (src/align.impala:190-216): one walk from get_score_pos() through the whole predecessor
+    matrix.  For EVERY scheme the emitted columns score exactly the optimum (the linear-space path only
+    guarantees that for global), de-gapped rows are substrings starting at get_alignment_start(), gap_init = 0
+    of the Gotoh variant is the reference path, and the frozen fixtures hold."""
+    rng = np.random.default_rng(77)
+    ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for (m, n) in [(1, 1), (3, 40), (200, 150), (700, 1300), (1500, 40)]:
+        q = ACGT[rng.integers(0, 4, m)]
+        s = ACGT[rng.integers(0, 4, n)]
+        k = min(m, n) // 2
+        s[n - k:] = q[:k]                                     # overlap: suffix of s = prefix of q
+        for mode in MODES:
+            for (gi, ge) in [(0, -1), (-2, -1), (-5, -2)]:
+                sc, aq, as_, st = oracle.traceback_full(mode, q, s, 2, -1, gi, ge)
+                want = oracle.score_linear(mode, q, s, 2, -1, ge) if gi == 0 else oracle.score_affine(mode, q, s, 2, -1, gi, ge)
+                assert sc == want[0]
+                col = oracle.column_score(aq, as_, 2, -1, ge) if gi == 0 else oracle.column_score_affine(aq, as_, 2, -1, gi, ge)
+                a = np.frombuffer(aq, np.uint8); b = np.frombuffer(as_, np.uint8)
+                nonblank = int(((a != 32) | (b != 32)).sum())
+                assert col == sc or (nonblank == 0 and sc <= 0), (m, n, mode, gi, col, sc)
+                dq = bytes(a[(a != 32) & (a != 95)]); ds = bytes(b[(b != 32) & (b != 95)])
+                assert bytes(q)[st[0]:st[0] + len(dq)] == dq and bytes(s)[st[1]:st[1] + len(ds)] == ds
+                if nonblank:
+                    assert (st[0] + len(dq) - 1, st[1] + len(ds) - 1) == tuple(want[1:])     # ends at get_score_pos()
+                if mode == "global":
+                    assert dq == bytes(q) and ds == bytes(s)
+    for c in golden["cases"]:
+        q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
+        for mode in MODES:
+            t = c["traceback_full"][mode]
+            sc, aq, as_, st = oracle.traceback_full(mode, q, s)
+            assert (sc, list(st), hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16]) == (t["score"], t["start"], t["sha"])
+            sc, aq, as_, st = oracle.traceback_full(mode, q, s, 2, -1, -2, -1)
+            assert (sc, list(st), hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16]) == \
+                   (t["affine"]["score"], t["affine"]["start"], t["affine"]["sha"])
+
+
 def test_affine_traceback_is_optimal_global(oracle):
     """build-defined Gotoh traceback (parity unpinned vs the reference): for the global scheme the emitted
     alignment must be a valid optimal one -- de-gapped rows reproduce the inputs and the affine column score
