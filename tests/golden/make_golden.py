@@ -77,6 +77,11 @@ def main():
                                     "column_score": O.column_score(aq, as_),
                                     "aq": aq.decode("latin-1") if len(aq) <= 2000 else None,
                                     "as": as_.decode("latin-1") if len(as_) <= 2000 else None}
+            # Gotoh linear-space traceback (build-defined, parity unpinned vs the reference): frozen all the same
+            ret, aq, as_, sp, ty = O.traceback_lintime_affine(mode, qq, ss, 2, -1, -2, -1)
+            c.setdefault("traceback_affine", {})[mode] = {"ret": ret, "sha": sha(aq, as_), "splits": sp.tolist(),
+                                                          "types": ty.tolist(),
+                                                          "column_score": O.column_score_affine(aq, as_, 2, -1, -2, -1)}
             # traceback_full (src/align.impala:190-216); "affine" = build-defined Gotoh variant (2,-1,-2,-1)
             sc, aq, as_, st = O.traceback_full(mode, qq, ss)
             assert sc == O.score_linear(mode, qq, ss)[0]

@@ -262,6 +262,7 @@ def test_split_ranks_equal_single_run(aligner, oracle):
 
 # --------------------------------------------------------------------------- tracebacks
 def test_traceback_golden_fixtures(aligner, golden):
+    import anyseq_b200 as A
     for c in golden["cases"]:
         q, s = c["q"].encode("latin-1"), c["s"].encode("latin-1")
         for mode in MODES:
@@ -271,6 +272,10 @@ def test_traceback_golden_fixtures(aligner, golden):
             assert _sha(r.aligned_query, r.aligned_subject) == t["sha"], (c["name"], mode)
             if t["aq"] is not None:
                 assert r.aligned_query == t["aq"].encode("latin-1") and r.aligned_subject == t["as"].encode("latin-1")
+            ta = c["traceback_affine"][mode]            # build-defined Gotoh traceback, frozen
+            r = aligner.align(mode, q, s, A.affine_scoring_scheme(2, -1, -2, -1))
+            assert aligner.last_splits() == ta["splits"] and aligner.last_split_types() == ta["types"], (c["name"], mode)
+            assert _sha(r.aligned_query, r.aligned_subject) == ta["sha"], (c["name"], mode, "affine")
 
 
 @pytest.mark.parametrize("m,n", [(300, 70), (1, 200), (200, 129), (5000, 9000), (9000, 5000), (2500, 16385),

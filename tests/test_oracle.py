@@ -147,6 +147,12 @@ def test_golden_fixtures(oracle, golden):
             ret, aq, as_, sp = oracle.traceback_lintime(mode, q, s)
             assert ret == t["ret"] and sp.tolist() == t["splits"]
             assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == t["sha"]
+            ta = c["traceback_affine"][mode]
+            ret, aq, as_, sp, ty = oracle.traceback_lintime_affine(mode, q, s, 2, -1, -2, -1)
+            assert (ret, sp.tolist(), ty.tolist()) == (ta["ret"], ta["splits"], ta["types"])
+            assert hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16] == ta["sha"]
+            if mode == "global":
+                assert ta["column_score"] == c["affine"]["global"]["2,-1,-2,-1"]
 
 
 def test_traceback_full_properties_and_fixtures(oracle, golden):
