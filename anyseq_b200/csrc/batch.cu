@@ -14,28 +14,12 @@
 // data-path collective.
 #include "engine.cuh"
 #include "strip_kernel.cuh"
+#include "batch.cuh"
 
 #include <algorithm>
 #include <cstring>
 
 namespace anyseq {
-
-struct BatchArgs {
-    const uint8_t* q;
-    const long long* qoff;
-    const uint8_t* s;
-    const long long* soff;
-    long long npairs;
-    int* scores;
-    ScoreParams sp;
-    int gap_init;
-    int mode;
-    int one;
-    int ncodes;
-    int cols_longer;               // 1: columns = longer sequence of a pair, 0: shorter
-    const uint8_t* lut;            // byte -> code (shared by both sequences)
-    unsigned long long* counter;   // next pair to claim
-};
 
 // stats[0] = max over pairs of max(lenq, lens), stats[1] = max over pairs of min(lenq, lens)
 __global__ void batch_stats_kernel(const long long* __restrict__ qoff, const long long* __restrict__ soff,
@@ -211,7 +195,6 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
     }
 }
 
-using BatchKernelFn = void (*)(const BatchArgs);
 
 template <int MODE, bool AFFINE>
 static BatchKernelFn pick_batch_kernel_k(int K, bool mask)
@@ -284,13 +267,31 @@ int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, con
     }
     int K = 4;
     while (32 * K < ncols) K *= 2;
-    BatchKernelFn fn = pick_batch_kernel(sc.mode, affine, K, use_mask_);
+    // Packed 16-bit kernels (batch_x2.cu, two pairs per warp): only when every value a pair of these lengths can
+    // produce fits a non-negative 16-bit half after adding `bias` (see batch_x2.cu).  Bounds: any cell is at least
+    // the all-gap path 2 gi + (rows + cols + 2) ge, at most same * min(rows, cols); columns are padded to 32 K.
+    int bias = 0;
+    bool packed = false;
+    if (use_mask_ && tune.batch_packed) {
+        const long long rows_max = cols_longer ? max_short : max_long;
+        const long long cols_pad = 32LL * K;
+        const long long go = affine ? sp.gap_open : 0;
+        const long long hmin = 2LL * sc.gap_init + (rows_max + cols_pad + 2) * sc.gap_extend;
+        const long long lowest = hmin + go + std::min<long long>(0, std::min(sc.same, sc.diff));
+        const long long hmax = std::max<long long>(sc.same, 0) * std::min(rows_max, cols_pad);
+        const long long b = -lowest + 8;
+        const long long small = std::max<long long>({std::llabs(sc.same), std::llabs(sc.diff), std::llabs(go), std::llabs(sc.gap_extend)});
+        if (b + hmax + 2 * small < 32000 && small < 2000) { packed = true; bias = (int)b; }
+    }
+    BatchKernelFn fn = packed ? pick_batch_x2_kernel(sc.mode, affine, K) : pick_batch_kernel(sc.mode, affine, K, use_mask_);
     if (!fn) { set_last_error("no batch kernel for this configuration"); return ANYSEQ_ERR_UNSUPPORTED; }
-    const size_t dyn = use_mask_ ? sizeof(unsigned) * 32 * (size_t)ncodes_ * kWarpsPerBlock : 0;
+    // packed: two mask sets, match bits spread to every other bit (2 K bits per lane and row)
+    const size_t dyn = use_mask_ ? sizeof(unsigned) * 32 * (size_t)ncodes_ * kWarpsPerBlock * (packed ? 2 * ((2 * K + 31) / 32) : 1) : 0;
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn));
     if (nb < 1) { set_last_error("batch kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
-    const int grid = (int)std::min<long long>((long long)nb * sm_count, (npairs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const long long units = packed ? (npairs + 1) / 2 : npairs;      // work items claimed by the warps
+    const int grid = (int)std::min<long long>((long long)nb * sm_count, (units + kWarpsPerBlock - 1) / kWarpsPerBlock);
     BatchArgs ba;
     ba.q = d_q;
     ba.qoff = reinterpret_cast<const long long*>(d_qoff);
@@ -304,6 +305,7 @@ int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, con
     ba.one = 1;
     ba.ncodes = ncodes_;
     ba.cols_longer = cols_longer;
+    ba.bias = bias;
     ba.lut = lut_.as<uint8_t>();
     ba.counter = reinterpret_cast<unsigned long long*>(misc_.as<int>() + kMiscCounter);
     const unsigned long long first = (unsigned long long)grid * kWarpsPerBlock;

@@ -121,7 +121,8 @@ int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int block
  * "force_generic" (1: byte-register kernels even for small alphabets),
  * "align_with_score" (0: anyseq_align skips the extra score pass),
  * "batch_chunk_bytes" / "batch_chunk_pairs" / "batch_copy_threads" (pipeline of
- * anyseq_score_batch with host buffers),
+ * anyseq_score_batch with host buffers), "batch_packed" (0: never use the 16-bit two-pairs-per-warp
+ * batch kernels),
  * "local_end_cell" (1: local scores also fill end_i/end_j with the cell the
  * reference's get_score_pos() reports -- src/scoring.impala:103-110 with the
  * slot order of src/scoring_cpu.impala:48-73; runs the single-row kernels,

@@ -608,3 +608,37 @@ def test_traceback_full_large_and_refusal(aligner):
     with pytest.raises(A.AnyseqError) as e:
         aligner.align_full("global", big, big)
     assert e.value.code == -4
+
+
+def test_batch_packed_16bit_kernels(aligner, oracle):
+    """two pairs per warp in 16-bit halves (batch_x2.cu): uniform shapes (every warp packs two DIFFERENT pairs), all
+    schemes, linear + Gotoh, odd pair count, large costs near the eligibility bound; must equal the 32-bit kernels
+    (option batch_packed = 0) everywhere and the oracle on a sample"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(21)
+    for (lq, ls, npairs) in [(150, 500, 2001), (37, 90, 501), (1000, 1024, 65), (64, 64, 300), (500, 150, 400)]:
+        qs, ss = [], []
+        for p in range(npairs):
+            q = _rand(rng, lq); s = _rand(rng, ls)
+            k = min(lq, ls)
+            if p % 3:
+                o = int(rng.integers(0, max(ls - k, 0) + 1))
+                s[o:o + k] = q[:k]
+                s[rng.integers(0, ls, max(1, ls // 15))] = ACGT[p % 4]
+            qs.append(q); ss.append(s)
+        qd, qo = _pack(qs); sd, so = _pack(ss)
+        for sch in (A.affine_scoring_scheme(2, -1, -2, -1), A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(5, -4, -10, -1),
+                    A.linear_scoring_scheme(3, -2, -4)):
+            for mode in MODES:
+                aligner.set_option("batch_packed", 1)
+                got, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)
+                aligner.set_option("batch_packed", 0)
+                ref, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)
+                aligner.set_option("batch_packed", 1)
+                assert (got == ref).all(), (lq, ls, mode, sch, np.flatnonzero(got != ref)[:5])
+                for p in (0, 1, npairs // 2, npairs - 2, npairs - 1):
+                    if sch.affine:
+                        want = oracle.score_affine(mode, qs[p], ss[p], sch.same, sch.diff, sch.gap_init, sch.gap_extend)[0]
+                    else:
+                        want = oracle.score_linear(mode, qs[p], ss[p], sch.same, sch.diff, sch.gap_extend)[0]
+                    assert got[p] == want, (lq, ls, mode, sch, p)
