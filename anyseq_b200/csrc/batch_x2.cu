@@ -82,6 +82,22 @@ struct CellX2 {
     }
 };
 
+// colbest = max(colbest, X[idx]) for a warp-uniform run-time idx: a jump into K one-instruction cases instead of
+// K compare/select pairs per row
+template <int K>
+__device__ __forceinline__ void max_column_u(unsigned& best, const unsigned (&X)[K], int idx)
+{
+    switch (idx) {
+#define ANYSEQ_CASE(c) case c: if constexpr (c < K) best = __vmaxs2(best, X[c < K ? c : 0]); break;
+        ANYSEQ_CASE(0) ANYSEQ_CASE(1) ANYSEQ_CASE(2) ANYSEQ_CASE(3) ANYSEQ_CASE(4) ANYSEQ_CASE(5) ANYSEQ_CASE(6) ANYSEQ_CASE(7)
+        ANYSEQ_CASE(8) ANYSEQ_CASE(9) ANYSEQ_CASE(10) ANYSEQ_CASE(11) ANYSEQ_CASE(12) ANYSEQ_CASE(13) ANYSEQ_CASE(14) ANYSEQ_CASE(15)
+        ANYSEQ_CASE(16) ANYSEQ_CASE(17) ANYSEQ_CASE(18) ANYSEQ_CASE(19) ANYSEQ_CASE(20) ANYSEQ_CASE(21) ANYSEQ_CASE(22) ANYSEQ_CASE(23)
+        ANYSEQ_CASE(24) ANYSEQ_CASE(25) ANYSEQ_CASE(26) ANYSEQ_CASE(27) ANYSEQ_CASE(28) ANYSEQ_CASE(29) ANYSEQ_CASE(30) ANYSEQ_CASE(31)
+#undef ANYSEQ_CASE
+        default: break;
+    }
+}
+
 template <int K>
 __device__ __forceinline__ unsigned pick_column_u(const unsigned (&X)[K], int idx)
 {
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                             hr = st.xleft;
                             er = st.e;
                             if constexpr (MODE == kSemiglobal) {
-                                if (lane == outlane) colbest = __vmaxs2(colbest, pick_column_u<K>(X, outc));
+                                if (lane == outlane) max_column_u<K>(colbest, X, outc);
                             }
                         }
 #pragma unroll
