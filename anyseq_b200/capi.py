@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libanyseq_b200.so")
+LIB_PATH = os.environ.get("ANYSEQ_LIB") or os.path.join(_HERE, "_build", "libanyseq_b200.so")   # ANYSEQ_LIB: kernel-variant experiments
 
 GLOBAL, SEMIGLOBAL, LOCAL = 0, 1, 2
 MODES = {"global": GLOBAL, "semiglobal": SEMIGLOBAL, "local": LOCAL}
