@@ -181,7 +181,7 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool trac
 static int rows_per_step(int K, bool mask, bool track)
 {
     if (!mask || track) return 1;      // end-cell tracking runs on the single-row kernels
-    return K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1);
+    return K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : (K >= 8 ? ANYSEQ_ROWS_K8 : ANYSEQ_ROWS_K4));
 }
 
 // CTAs per SM actually launched.  Multi-row tiles carry R dependent chains per
@@ -342,15 +342,15 @@ int Engine::pick_K(int n) const
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
     // At most one warp works on a strip at a time, so the strips must at least
-    // cover the warps the kernel variant runs with (2 CTAs/SM = 1184 warps for the
-    // two-row tile kernels, 3552 for the narrow single-row ones); beyond that,
-    // wider strips have less per-step overhead.  Thresholds from B200
-    // measurements (profiles/): n = 575 k runs 2.8 TCUPS at K=16 and 1.7 at K=32, n = 1.15 M
-    // 3.3 at K=16 and 3.1 at K=32, n = 2.3 M 3.6 at K=32.
+    // cover the warps the kernel variant runs with; beyond that, wider strips have
+    // less per-step overhead.  Thresholds from B200 measurements (profiles/), semiglobal
+    // Gotoh, GCUPS: n = 100 k: 1116 at K=8 (four-row tiles) vs 640 at K=16; 400 k: 2345 vs 1887;
+    // 575 k: 2859 vs 2711; 800 k: 2904 vs 2807; 1.15 M: 2954 vs 3196 at K=16 (3100 at K=32);
+    // 2.3 M: 3600 at K=32.
     if (use_mask_) {
         if (n >= 1800000) return 32;
-        if (n >= 280000) return 16;
-        if (n >= 70000) return 8;
+        if (n >= 1000000) return 16;
+        if (n >= 40000) return 8;
         return 4;
     }
     if (n >= 1500000) return 16;      // generic kernels keep subject bytes in registers: K <= 16

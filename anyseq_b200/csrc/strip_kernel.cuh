@@ -758,9 +758,15 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #ifndef ANYSEQ_ROWS_K16
 #define ANYSEQ_ROWS_K16 2
 #endif
+#ifndef ANYSEQ_ROWS_K8
+#define ANYSEQ_ROWS_K8 4     // narrow problems have few strips: four chains per warp make the lone warps fast
+#endif
+#ifndef ANYSEQ_ROWS_K4
+#define ANYSEQ_ROWS_K4 1
+#endif
 template <int K, bool MASK>
 struct StripRows {
-    static constexpr int value = !MASK ? 1 : (K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : 1));
+    static constexpr int value = !MASK ? 1 : (K >= 32 ? ANYSEQ_ROWS_K32 : (K >= 16 ? ANYSEQ_ROWS_K16 : (K >= 8 ? ANYSEQ_ROWS_K8 : ANYSEQ_ROWS_K4)));
 };
 
 // CTAs per SM the register allocation is capped for.  Single-row kernels need
@@ -772,7 +778,7 @@ constexpr int strip_min_blocks()
 {
     constexpr int R = StripRows<K, MASK>::value;
     if (R >= 4) return 1;
-    if (R == 2) return K >= 32 ? 2 : 3;
+    if (R == 2) return K >= 32 ? 2 : (K >= 16 ? 3 : 4);
     return K >= 32 ? 4 : (K >= 16 ? 5 : 6);
 }
 
