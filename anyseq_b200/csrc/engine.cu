@@ -336,7 +336,7 @@ int Engine::analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s
     return ANYSEQ_OK;
 }
 
-int Engine::pick_K(int n) const
+int Engine::pick_K(int n, bool chained) const
 {
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
@@ -349,8 +349,11 @@ int Engine::pick_K(int n) const
     // 2.3 M: 3600 at K=32.
     if (use_mask_) {
         if (n >= 1800000) return 32;
-        if (n >= 1000000) return 16;
-        if (n >= 40000) return 8;
+        // A slice of a multi-GPU wavefront also sits in a chain over the ranks, whose fill time grows with
+        // strips x rows of lag: K = 8 (twice the strips, 224 rows of lag) cost 1458 vs 1169 ms per alignment on
+        // 8 GPUs although the slice alone is 5 % faster -- chained slices keep the wider strips.
+        if (n >= (chained ? 280000 : 1000000)) return 16;
+        if (n >= (chained ? 70000 : 40000)) return 8;
         return 4;
     }
     if (n >= 1500000) return 16;      // generic kernels keep subject bytes in registers: K <= 16
@@ -505,7 +508,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     rc = analyse_alphabet(d_q, m, d_s_slice, w);
     if (rc) return rc;
-    const int K = want_edges_ ? 4 : pick_K(w);     // edge columns are wanted per 128-column block
+    const int K = want_edges_ ? 4 : pick_K(w, inbox != nullptr || next_inbox != nullptr);     // edge columns are wanted per 128-column block
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
     const int resident = resident_warps(K, local, affine, nstrips);

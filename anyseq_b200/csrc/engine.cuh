@@ -112,7 +112,7 @@ public:
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
                  int* launches);
-    int pick_K(int n) const;
+    int pick_K(int n, bool chained = false) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int pick_band(int m, int nstrips, int resident, int K) const;
 
