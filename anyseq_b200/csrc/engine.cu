@@ -293,7 +293,7 @@ void Engine::destroy()
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
                             &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
-                            &batch_q_, &batch_s_, &batch_qoff_, &batch_soff_, &batch_scores_, &blockmax_, &edges_};
+                            &tb_out_, &blockmax_, &edges_};
     drop_host_batch_stream();
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);

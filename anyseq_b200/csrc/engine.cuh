@@ -123,7 +123,7 @@ private:
     DeviceBuffer lut_;                // byte -> code tables of the MASK kernels + presence bits
     DeviceBuffer col2_;               // second column-record set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
-    DeviceBuffer batch_q_, batch_s_, batch_qoff_, batch_soff_, batch_scores_;
+    DeviceBuffer tb_out_;             // linear-space traceback: the two output rows on the device
     DeviceBuffer edges_;         // full-matrix traceback: right edge column (H, E) of every 128-column strip
     DeviceBuffer blockmax_;      // local end-cell tracking: one key per 1024 x 1024 reference block
     int* h_misc_ = nullptr;           // pinned mirror of misc_

@@ -368,10 +368,10 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         blk[nb + b] = h;
     }
     if (aux2_.ensure(sizeof(int) * 2 * (size_t)nb) || pred_.ensure((size_t)m * 32 + 64) ||
-        batch_q_.ensure(2 * outlen + 64))
+        tb_out_.ensure(2 * outlen + 64))
         return ANYSEQ_ERR_NO_DEVICE;
     int* d_blk = aux2_.as<int>();
-    uint8_t* d_out = batch_q_.as<uint8_t>();
+    uint8_t* d_out = tb_out_.as<uint8_t>();
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(d_blk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_out, ' ', 2 * outlen, stream_));
     {

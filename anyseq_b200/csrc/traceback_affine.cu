@@ -389,11 +389,11 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
         blk[3 * nb + b] = types[s1 + 1];               // end vertex type
         blk[4 * nb + b] = 0;
     }
-    if (aux2_.ensure(sizeof(int) * 7 * (size_t)nb) || pred_.ensure((size_t)m * 64 + 128) || batch_q_.ensure(2 * outlen + 64))
+    if (aux2_.ensure(sizeof(int) * 7 * (size_t)nb) || pred_.ensure((size_t)m * 64 + 128) || tb_out_.ensure(2 * outlen + 64))
         return ANYSEQ_ERR_NO_DEVICE;
     int* d_blk = aux2_.as<int>();
     int* d_blk_end = d_blk + 5 * nb;
-    uint8_t* d_out = batch_q_.as<uint8_t>();
+    uint8_t* d_out = tb_out_.as<uint8_t>();
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(d_blk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_blk_end, 0, sizeof(int) * 2 * (size_t)nb, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_out, ' ', 2 * outlen, stream_));

@@ -48,6 +48,10 @@ def test_sass_is_sm100a_with_dpx():
     if "VIADDMNMX" not in sass:     # older cuobjdump: fall back to a whole-file dump
         sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "VIADDMNMX" in sass and "VIMNMX3" in sass and "IMAD" in sass
+    # packed batch kernels: two 16-bit cells per DPX instruction, predicates from R2P
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq15batch_x2_kernelILi1ELb1ELi16EEEvNS_9BatchArgsE",
+                           capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "VIADDMNMX.S16x2" in sass and "VIMNMX3.S16x2" in sass and "R2P" in sass
 
 
 def test_no_cpu_fallback():
