@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "anyseq_batch_stream_open", "anyseq_batch_stream_acquire", "anyseq_batch_stream_submit", "anyseq_batch_stream_finish",
     "anyseq_batch_stream_collect", "anyseq_batch_stream_release", "anyseq_batch_stream_stats", "anyseq_batch_stream_close",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
-    "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_strip_combine",
+    "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_score_strip_device_multi", "anyseq_strip_combine",
     "anyseq_measure_int_peak", "anyseq_device_info",
 ]
 
@@ -144,6 +144,10 @@ def load_library(path: str | None = None):
     L.anyseq_score_strip_device.restype = C.c_int
     L.anyseq_score_strip_device.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                             vp, vp, C.POINTER(StripPartial)]
+    L.anyseq_score_strip_device_multi.restype = C.c_int
+    L.anyseq_score_strip_device_multi.argtypes = [vp, C.POINTER(Scoring), C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
+                                                  C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                                  C.POINTER(StripPartial)]
     L.anyseq_strip_combine.restype = C.c_int
     L.anyseq_strip_combine.argtypes = [C.POINTER(Scoring), C.POINTER(StripPartial), C.c_int, C.POINTER(Result)]
     L.anyseq_measure_int_peak.restype = C.c_int

@@ -225,6 +225,29 @@ int anyseq_score_strip_device(anyseq_ctx* ctx, const anyseq_scoring* sc, const v
                                        next_inbox ? &next_inbox->box : nullptr, out);
 }
 
+int anyseq_score_strip_device_multi(anyseq_ctx* ctx, const anyseq_scoring* sc, int npairs, const void* const* d_query,
+                                    int lenq, const void* const* d_subject_slice, int col_begin, int col_end,
+                                    int lens_total, anyseq_inbox* const* inbox, anyseq_inbox* const* next_inbox,
+                                    anyseq_strip_partial* out)
+{
+    if (!ctx || !sc || !out || npairs < 1 || npairs > 8 || !d_query || !d_subject_slice) return ANYSEQ_ERR_BAD_ARG;
+    const uint8_t* q[8];
+    const uint8_t* s[8];
+    anyseq::Inbox* in[8];
+    anyseq::Inbox* nx[8];
+    bool any_in = false, any_nx = false;
+    for (int p = 0; p < npairs; ++p) {
+        q[p] = static_cast<const uint8_t*>(d_query[p]);
+        s[p] = static_cast<const uint8_t*>(d_subject_slice[p]);
+        in[p] = (inbox && inbox[p]) ? &inbox[p]->box : nullptr;
+        nx[p] = (next_inbox && next_inbox[p]) ? &next_inbox[p]->box : nullptr;
+        any_in |= in[p] != nullptr;
+        any_nx |= nx[p] != nullptr;
+    }
+    return ctx->eng.score_strip_device_multi(*sc, npairs, q, lenq, s, col_begin, col_end, lens_total,
+                                             any_in ? in : nullptr, any_nx ? nx : nullptr, out);
+}
+
 // Combine per-rank partial results exactly as a single-GPU run would
 // (src/scoring.impala:29-137): global = H(m-1,n-1) of the last rank;
 // semiglobal = last-row maximum first (lowest column, the -1 candidate with

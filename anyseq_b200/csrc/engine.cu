@@ -85,7 +85,8 @@ __device__ void arg_max_lowest(const int* __restrict__ v, int n, int stride, int
 __global__ void finish_score_kernel(const Job* __restrict__ jobs, int mode, int col0, int n_total,
                                     int* __restrict__ out)
 {
-    const Job J = jobs[0];
+    const Job J = jobs[blockIdx.x];          // one block per job, 8 result words each
+    out += 8 * blockIdx.x;
     int rv, ri, cv, ci;
     const int* colH = reinterpret_cast<const int*>(J.col);      // .x of every 16-byte record
     arg_max_lowest(J.rowH, J.w, 1, rv, ri);
@@ -293,7 +294,7 @@ void Engine::destroy()
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
                             &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
-                            &tb_out_, &blockmax_, &edges_};
+                            &tb_out_, &blockmax_, &edges_, &multi_};
     drop_host_batch_stream();
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
@@ -383,7 +384,7 @@ int Engine::pick_band(int m, int nstrips, int resident, int K) const
 
 // Launch init + strip kernels for a job list that is already in host memory.
 int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
-                     int* launches)
+                     int* launches, bool interleave)
 {
     const int njobs = (int)jobs.size();
     long long total = 0;
@@ -435,6 +436,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
         ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ka.next_item, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
     }
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
+    ka.interleave = interleave ? 1 : 0;
     void* args[] = {&ka};
     ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, dyn_smem, stream_));
     if (launches) *launches += 2;
@@ -600,6 +602,132 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
         out->local_best = h_misc_[kMiscBest];
         out->kernel_ms = ms;
         out->kernel_launches = launches;
+    }
+    return ANYSEQ_OK;
+}
+
+// Several pairs of one shape in ONE persistent launch (items ordered band, pair, strip).  Used by the streamed
+// multi-GPU wavefront: a rank's slice of two consecutive alignments gives the kernel twice the strips, so all
+// warps have work (one slice alone feeds 1.9 warps per scheduler, profiles/r01_summary.md).  Every pair has its
+// own border records, bottom rows, corners, progress counters, inboxes and partial result.
+int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const uint8_t* const* d_q, int m,
+                                     const uint8_t* const* d_s_slice, int col_begin, int col_end, int n_total,
+                                     Inbox* const* inbox, Inbox* const* next_inbox, anyseq_strip_partial* out)
+{
+    if (npairs < 1 || npairs > 8 || !d_q || !d_s_slice || !out) { set_last_error("bad pair list"); return ANYSEQ_ERR_BAD_ARG; }
+    if (npairs == 1)
+        return score_strip_device(sc, d_q[0], m, d_s_slice[0], col_begin, col_end, n_total, inbox ? inbox[0] : nullptr,
+                                  next_inbox ? next_inbox[0] : nullptr, out);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
+    ScoreParams sp;
+    bool affine;
+    int rc = make_score_params(sc, &sp, &affine);
+    if (rc) return rc;
+    const int w = col_end - col_begin;
+    if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
+    const bool local = sc.mode == ANYSEQ_LOCAL;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    // one alphabet for all pairs: presence bits accumulate over every sequence
+    {
+        if (lut_.ensure(512 + 64 + 16)) return ANYSEQ_ERR_NO_DEVICE;
+        unsigned* bits = reinterpret_cast<unsigned*>(lut_.as<uint8_t>() + 512);
+        int* d_ncodes = reinterpret_cast<int*>(bits + 16);
+        ANYSEQ_CUDA_CHECK(cudaMemsetAsync(bits, 0, sizeof(unsigned) * 17, stream_));
+        const int gq = (int)std::min<long long>(sm_count * 8, (m + 255) / 256);
+        const int gs = (int)std::min<long long>(sm_count * 8, (w + 255) / 256);
+        for (int p = 0; p < npairs; ++p) {
+            alphabet_presence_kernel<<<std::max(gq, 1), 256, 0, stream_>>>(d_q[p], m, bits);
+            alphabet_presence_kernel<<<std::max(gs, 1), 256, 0, stream_>>>(d_s_slice[p], w, bits + 8);
+        }
+        build_lut_kernel<<<1, 32, 0, stream_>>>(bits, bits + 8, lut_.as<uint8_t>(), lut_.as<uint8_t>() + 256, d_ncodes);
+        ANYSEQ_CUDA_CHECK(cudaGetLastError());
+        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_ + kMiscWords - 1, d_ncodes, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        ncodes_ = h_misc_[kMiscWords - 1];
+        use_mask_ = ncodes_ <= kMaxCodes && !tune.force_generic;
+        if (!use_mask_) ncodes_ = 1;
+    }
+    const bool chained = inbox != nullptr || next_inbox != nullptr;
+    // the strips of all pairs feed the warps together: choose the strip width for the combined width
+    const int K = pick_K((int)std::min<long long>((long long)w * npairs, 0x7fffffff), chained);
+    const int SW = kWarp * K;
+    const int nstrips = (w + SW - 1) / SW;
+    const long long strips_all = (long long)nstrips * npairs;
+    const int resident = resident_warps(K, local, affine, strips_all);
+    // the window of resident warps spans the strips of ALL pairs of a band
+    const int band_h = pick_band(m, (int)std::min<long long>(strips_all, 0x7fffffff), resident, K);
+
+    // per-pair storage carved out of one buffer: col records, rowH, rowF, corner, progress, result words
+    const size_t wpad = (size_t)nstrips * SW;
+    auto align256 = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_col = align256(sizeof(int4) * (size_t)m), b_row = align256(sizeof(int) * wpad),
+                 b_small = align256(sizeof(int) * (size_t)nstrips);
+    const size_t per_pair = b_col + 2 * b_row + 2 * b_small;
+    const size_t b_res = align256(sizeof(int) * 16 * (size_t)npairs);
+    if (multi_.ensure(per_pair * (size_t)npairs + b_res)) return ANYSEQ_ERR_NO_DEVICE;
+    uint8_t* base = multi_.as<uint8_t>();
+    int* d_res = reinterpret_cast<int*>(base + per_pair * (size_t)npairs);       // [npairs][8] finish words, then [npairs] best
+    int* d_best = d_res + 8 * npairs;
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_res, 0, b_res, stream_));
+
+    std::vector<Job> jobs((size_t)npairs);
+    for (int p = 0; p < npairs; ++p) {
+        Job& J = jobs[(size_t)p];
+        std::memset(&J, 0, sizeof(J));
+        uint8_t* pb = base + per_pair * (size_t)p;
+        J.q = d_q[p];
+        J.s = d_s_slice[p];
+        J.h = m;
+        J.w = w;
+        J.band_h = band_h;
+        J.nstrips = nstrips;
+        J.nbands = (m + band_h - 1) / band_h;
+        J.col = reinterpret_cast<int4*>(pb);
+        J.rowH = reinterpret_cast<int*>(pb + b_col);
+        J.rowF = affine ? reinterpret_cast<int*>(pb + b_col + b_row) : nullptr;
+        J.corner = reinterpret_cast<int*>(pb + b_col + 2 * b_row);
+        J.progress = reinterpret_cast<int*>(pb + b_col + 2 * b_row + b_small);
+        J.best = d_best + p;
+        J.init_global = sc.mode == ANYSEQ_GLOBAL;
+        J.top_open = sp.gap_open;
+        Inbox* in = inbox ? inbox[p] : nullptr;
+        Inbox* nx = next_inbox ? next_inbox[p] : nullptr;
+        if (in) { J.in = in->records; J.in_tag = 0x40000000 + (++in->uses_in & 0xffffff); }
+        if (nx) { J.out = nx->records; J.out_tag = 0x40000000 + (++nx->uses_out & 0xffffff); }
+    }
+    int launches = 2 * npairs + 1;   // alphabet analysis
+    init_col0_ = col_begin;
+    rc = run_jobs(jobs, sp, local, affine, K, &launches, /*interleave=*/true);
+    init_col0_ = 0;
+    if (rc) return rc;
+    finish_score_kernel<<<npairs, 1024, 0, stream_>>>(jobs_.as<Job>(), sc.mode, col_begin, n_total, d_res);
+    ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    launches += 1;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    std::vector<int> h_res((size_t)9 * npairs);
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_res.data(), d_res, sizeof(int) * 9 * (size_t)npairs, cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_, misc_.ptr, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (h_misc_[kMiscStatus] != kStatusOk) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "strip kernel watchdog fired (status %d, need %d, saw %d)",
+                      h_misc_[kMiscStatus], h_misc_[kMiscStatus + 1], h_misc_[kMiscStatus + 2]);
+        set_last_error(buf);
+        return ANYSEQ_ERR_KERNEL_TIMEOUT;
+    }
+    float ms = 0.f;
+    ANYSEQ_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    for (int p = 0; p < npairs; ++p) {
+        const int* r = h_res.data() + 8 * p;
+        out[p].row_best = r[3];
+        out[p].row_best_j = r[4];
+        out[p].col_best = r[5];
+        out[p].col_best_i = r[6];
+        out[p].corner = r[7];
+        out[p].local_best = h_res[(size_t)8 * npairs + p];
+        out[p].kernel_ms = ms;
+        out[p].kernel_launches = p == 0 ? launches : 0;
     }
     return ANYSEQ_OK;
 }

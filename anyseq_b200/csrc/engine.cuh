@@ -78,6 +78,11 @@ public:
     int score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int m,
                            const uint8_t* d_s_slice, int col_begin, int col_end, int n_total,
                            Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out);
+    // several pairs of the SAME shape (lenq, slice) in one launch, their items interleaved band by band: a narrow
+    // multi-GPU slice has too few strips to fill the SMs, two of them side by side do (engine.cu)
+    int score_strip_device_multi(const anyseq_scoring& sc, int npairs, const uint8_t* const* d_q, int m,
+                                 const uint8_t* const* d_s_slice, int col_begin, int col_end, int n_total,
+                                 Inbox* const* inbox, Inbox* const* next_inbox, anyseq_strip_partial* out);
     int align_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                    char* alq, char* als, anyseq_result* out);
     int align_host_affine(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
@@ -111,7 +116,7 @@ public:
 
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
-                 int* launches);
+                 int* launches, bool interleave = false);
     int pick_K(int n, bool chained = false) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int pick_band(int m, int nstrips, int resident, int K) const;
@@ -124,6 +129,7 @@ private:
     DeviceBuffer col2_;               // second column-record set (Hirschberg right halves)
     DeviceBuffer aux_, aux2_, pred_;  // traceback scratch
     DeviceBuffer tb_out_;             // linear-space traceback: the two output rows on the device
+    DeviceBuffer multi_;         // score_strip_device_multi: per-pair border/row/corner/progress/result storage
     DeviceBuffer edges_;         // full-matrix traceback: right edge column (H, E) of every 128-column strip
     DeviceBuffer blockmax_;      // local end-cell tracking: one key per 1024 x 1024 reference block
     int* h_misc_ = nullptr;           // pinned mirror of misc_

@@ -53,6 +53,8 @@ struct KernelArgs {
     int* status;                    // [0] StatusCode, [1..3] diagnostics
     unsigned long long* next_item;  // work counter, initialised to the number of resident warps
     unsigned long long timeout_ns;  // watchdog for dependency waits
+    int interleave;                 // != 0: all jobs have the same nstrips / nbands and items are ordered
+                                    // (band, job, strip) instead of (job, band, strip): the jobs advance together
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -813,11 +815,21 @@ strip_kernel(const KernelArgs a)
     int jcur = 0;
     long long item = (long long)blockIdx.x * kWarpsPerBlock + warp;
     for (; item < a.total_items;) {
-        while (jcur + 1 < a.njobs && item >= a.jobs[jcur + 1].item_begin) ++jcur;
+        int band, strip;
+        if (a.interleave) {
+            const int ns = a.jobs[0].nstrips;
+            const long long per_band = (long long)a.njobs * ns;
+            band = (int)(item / per_band);
+            const int rem = (int)(item % per_band);
+            jcur = rem / ns;
+            strip = rem % ns;
+        } else {
+            while (jcur + 1 < a.njobs && item >= a.jobs[jcur + 1].item_begin) ++jcur;
+            const long long loc = item - a.jobs[jcur].item_begin;
+            band = (int)(loc / a.jobs[jcur].nstrips);
+            strip = (int)(loc % a.jobs[jcur].nstrips);
+        }
         const Job& J = a.jobs[jcur];
-        const long long loc = item - J.item_begin;
-        const int band = (int)(loc / J.nstrips);
-        const int strip = (int)(loc % J.nstrips);
         const bool partial = (strip + 1) * SW > J.w;
         bool ok;
         if (partial)

@@ -103,15 +103,19 @@ class StripWavefront:
     before any rank starts run k + 1 (the caller puts a barrier between runs).  depth >= 2:
     back-to-back runs are flow-controlled by RunTokens and overlap (no barrier between runs)."""
 
-    def __init__(self, aligner: Aligner, rank: int, world: int, rows: int, dist=None, depth: int = 1):
+    def __init__(self, aligner: Aligner, rank: int, world: int, rows: int, dist=None, depth: int = 1,
+                 pairs_per_launch: int = 1):
+        """pairs_per_launch > 1: run_multi() relaxes that many alignments of one shape in a single launch (a narrow
+        slice alone cannot fill a B200); every launch then uses its own set of pairs_per_launch inboxes."""
         self.al, self.rank, self.world, self.rows, self.dist = aligner, rank, world, rows, dist
         self.depth = max(1, int(depth)) if world > 1 else 1
+        self.ppl = max(1, int(pairs_per_launch))
         self._lib = capi.load_library()
-        self.inboxes = [C.c_void_p() for _ in range(self.depth)]
-        self.next_inboxes = [C.c_void_p() for _ in range(self.depth)]
+        self.inboxes = [C.c_void_p() for _ in range(self.depth * self.ppl)]
+        self.next_inboxes = [C.c_void_p() for _ in range(self.depth * self.ppl)]
         self.k = 0
         self.tokens = None
-        for d in range(self.depth):
+        for d in range(self.depth * self.ppl):
             handle = (C.c_ubyte * 64)()
             if world > 1 and rank > 0:
                 aligner._check(self._lib.anyseq_strip_inbox_create(aligner.handle, rows, C.byref(self.inboxes[d]), handle))
@@ -151,7 +155,8 @@ class StripWavefront:
         sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
         part = StripPartial()
         k = self.k
-        inbox, nxt = self.inboxes[k % self.depth], self.next_inboxes[k % self.depth]
+        slot = (k % self.depth) * self.ppl
+        inbox, nxt = self.inboxes[slot], self.next_inboxes[slot]
         if self.tokens is not None:
             self.tokens.acquire(k)
         self.al._check(self._lib.anyseq_score_strip_device(
@@ -161,6 +166,32 @@ class StripWavefront:
             self.tokens.release(k)
         self.k = k + 1
         return part
+
+    def run_multi(self, mode, scoring: ScoringScheme, d_queries, m: int, d_subject_slices,
+                  col_begin: int, col_end: int, n_total: int):
+        """len(d_queries) <= pairs_per_launch alignments of one shape in ONE launch -> list of StripPartial"""
+        npairs = len(d_queries)
+        if npairs < 1 or npairs > self.ppl or npairs != len(d_subject_slices):
+            raise ValueError("run_multi: between 1 and pairs_per_launch pairs")
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        k = self.k
+        slot = (k % self.depth) * self.ppl
+        vp = C.c_void_p
+        qs = (vp * npairs)(*[vp(int(x)) for x in d_queries])
+        ss = (vp * npairs)(*[vp(int(x)) for x in d_subject_slices])
+        has_in = bool(self.inboxes[slot])
+        has_nx = bool(self.next_inboxes[slot])
+        ins = (vp * npairs)(*[self.inboxes[slot + p] for p in range(npairs)]) if has_in else None
+        nxs = (vp * npairs)(*[self.next_inboxes[slot + p] for p in range(npairs)]) if has_nx else None
+        parts = (StripPartial * npairs)()
+        if self.tokens is not None:
+            self.tokens.acquire(k)
+        self.al._check(self._lib.anyseq_score_strip_device_multi(
+            self.al.handle, C.byref(sc), npairs, qs, m, ss, col_begin, col_end, n_total, ins, nxs, parts))
+        if self.tokens is not None:
+            self.tokens.release(k)
+        self.k = k + 1
+        return [StripPartial.from_buffer_copy(bytes(parts[p])) for p in range(npairs)]
 
     def combine(self, mode, scoring: ScoringScheme, part: StripPartial) -> AlignmentResult:
         """gather the per-rank partials and combine them exactly like a single-GPU run"""

@@ -168,6 +168,8 @@ def main():
                          "150000 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pairs-per-launch", type=int, default=4,
+                    help="N > 1, streamed steps: consecutive alignments relaxed side by side in one launch per rank")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="N > 1: barrier between steps (every alignment pays the full wavefront fill)")
     args = ap.parse_args()
@@ -215,7 +217,8 @@ def main():
     # N > 1: two inboxes per rank boundary, so consecutive alignments stream through the ranks back to
     # back (rank 0 starts pair k+1 while the wavefront of pair k is still inside the later ranks); the
     # neighbour-to-neighbour run tokens of multigpu.RunTokens replace a barrier between steps
-    wave = StripWavefront(al, rank, world, m, dist, depth=1 if args.no_pipeline else 2)
+    ppl = 1 if (world == 1 or args.no_pipeline) else max(1, args.pairs_per_launch)
+    wave = StripWavefront(al, rank, world, m, dist, depth=1 if args.no_pipeline else 2, pairs_per_launch=ppl)
     torch.cuda.synchronize()
 
     wave.reset()
@@ -228,9 +231,26 @@ def main():
         part = wave.run(MODE, scoring, d_q.data_ptr(), m, d_s.data_ptr(), c0, c1, n)
         return part
 
+    def launch_resident(npairs):
+        """npairs consecutive alignments of the stream in ONE launch per rank (N > 1: a slice alone cannot fill the GPU)"""
+        flush.zero_()
+        torch.cuda.synchronize()
+        return wave.run_multi(MODE, scoring, [d_q.data_ptr()] * npairs, m, [d_s.data_ptr()] * npairs, c0, c1, n)
+
+    def run_steps(count):
+        """-> (last partial, device ms summed over launches, kernel launches)"""
+        ms, nl, last, left = 0.0, 0, None, count
+        while left > 0:
+            k = min(ppl, left)
+            parts = launch_resident(k) if k > 1 else [step_resident()]
+            ms += parts[0].kernel_ms
+            nl += sum(p.kernel_launches for p in parts)
+            last = parts[-1]
+            left -= k
+        return last, ms, nl
+
     # ---- value: inputs resident in HBM -----------------------------------------
-    for _ in range(args.warmup):
-        part = step_resident()
+    part, _, _ = run_steps(args.warmup) if args.warmup > 0 else (None, 0, 0)
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -238,12 +258,7 @@ def main():
         sampler.start()
     t_wall0 = time.perf_counter()
     ev0.record()
-    dev_ms = 0.0
-    launches = 0
-    for _ in range(args.steps):
-        part = step_resident()
-        dev_ms += part.kernel_ms
-        launches += part.kernel_launches
+    part, dev_ms, launches = run_steps(args.steps)
     # wave.run() returns after its kernels have finished (the call synchronises its stream), so an event
     # on the idle torch stream is a device timestamp of "this rank's last step is done"
     ev1.record()
@@ -359,8 +374,10 @@ def main():
                               "CUDA events around the K steps on every rank, max over ranks"),
                    "steps_overlap": (None if world == 1 else
                                      ("no: barrier between steps" if args.no_pipeline else
-                                      "yes: consecutive alignments stream through the ranks back to back (double inboxes + "
-                                      "neighbour run tokens); single_alignment_ms is one alignment alone, barrier before it")),
+                                      f"yes: consecutive alignments stream through the ranks back to back ({ppl} per launch side by "
+                                      "side, one inbox each, two inbox sets + neighbour run tokens); single_alignment_ms is one "
+                                      "alignment alone, barrier before it")),
+                   "pairs_per_launch": ppl,
                    "single_alignment_ms": single_ms,
                    "single_alignment_gcups": (cells / (single_ms * 1e-3) / 1e9) if single_ms else None},
         "wall_ms_per_step": wall_ms_max / args.steps,

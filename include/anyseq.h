@@ -248,6 +248,15 @@ int anyseq_score_strip_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                               anyseq_inbox* inbox /* NULL on rank 0 */,
                               anyseq_inbox* next_inbox /* NULL on the last rank */,
                               anyseq_strip_partial* out);
+/* The same for `npairs` (<= 8) pairs of ONE shape (lenq, column range) in a single persistent launch, their work
+ * items interleaved band by band.  A narrow slice alone has too few strips to occupy a B200; the slices of two
+ * consecutive alignments of a stream side by side do.  Arrays of npairs device pointers / inboxes (inbox arrays may be
+ * NULL on the first / last rank); out[npairs]. */
+int anyseq_score_strip_device_multi(anyseq_ctx* ctx, const anyseq_scoring* sc, int npairs,
+                                    const void* const* d_query, int lenq,
+                                    const void* const* d_subject_slice, int col_begin, int col_end, int lens_total,
+                                    anyseq_inbox* const* inbox, anyseq_inbox* const* next_inbox,
+                                    anyseq_strip_partial* out);
 int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* parts, int nranks,
                          anyseq_result* out);
 

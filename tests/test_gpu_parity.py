@@ -260,6 +260,63 @@ def test_split_ranks_equal_single_run(aligner, oracle):
                 assert res.score == ref == aligner.score(mode, q, s, sch).score, (mode, sch, cut)
 
 
+def test_multi_pair_launch_equals_single_runs(aligner, oracle):
+    """anyseq_score_strip_device_multi: several DIFFERENT pairs of one shape in a single launch (items interleaved band by
+    band), alone and as the two emulated ranks of a wavefront with one inbox per pair; every pair must get exactly the
+    result of its own single run"""
+    import anyseq_b200 as A
+    from anyseq_b200 import capi
+    from anyseq_b200.capi import Result, StripPartial, make_scoring
+    import torch
+    L = capi.load_library()
+    vp = C.c_void_p
+    rng = np.random.default_rng(12)
+    m, n, cut, P = 6000, 9000, 4096, 3
+    qs = [_rand(rng, m) for _ in range(P)]
+    ss = [_related(rng, q, n, sub=0.05 + 0.03 * i) for i, q in enumerate(qs)]
+    dq = [torch.from_numpy(x).cuda() for x in qs]
+    ds = [torch.from_numpy(x).cuda() for x in ss]
+    aligner.tune(band_rows=1024, watchdog_ms=10000)          # several bands, so the interleaved order matters
+    try:
+        for sch in (A.affine_scoring_scheme(), A.linear_scoring_scheme(3, -2, -4)):
+            for mode in MODES:
+                sc = make_scoring(mode, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                want = [aligner.score(mode, q, s, sch).score for q, s in zip(qs, ss)]
+                # (a) whole width, no inbox
+                parts = (StripPartial * P)()
+                rc = L.anyseq_score_strip_device_multi(aligner.handle, C.byref(sc), P, (vp * P)(*[vp(t.data_ptr()) for t in dq]), m,
+                                                       (vp * P)(*[vp(t.data_ptr()) for t in ds]), 0, n, n, None, None, parts)
+                assert rc == 0, L.anyseq_last_error()
+                for p in range(P):
+                    res = Result()
+                    assert L.anyseq_strip_combine(C.byref(sc), C.byref(parts[p]), 1, C.byref(res)) == 0
+                    assert res.score == want[p], (mode, sch, p)
+                # (b) two emulated ranks, one inbox per pair
+                boxes = [vp() for _ in range(P)]
+                for b in boxes:
+                    assert L.anyseq_strip_inbox_create(aligner.handle, m, C.byref(b), None) == 0
+                left = (StripPartial * P)()
+                right = (StripPartial * P)()
+                rc = L.anyseq_score_strip_device_multi(aligner.handle, C.byref(sc), P, (vp * P)(*[vp(t.data_ptr()) for t in dq]), m,
+                                                       (vp * P)(*[vp(t.data_ptr()) for t in ds]), 0, cut, n, None, (vp * P)(*boxes), left)
+                assert rc == 0, L.anyseq_last_error()
+                rc = L.anyseq_score_strip_device_multi(aligner.handle, C.byref(sc), P, (vp * P)(*[vp(t.data_ptr()) for t in dq]), m,
+                                                       (vp * P)(*[vp(t.data_ptr() + cut) for t in ds]), cut, n, n, (vp * P)(*boxes), None,
+                                                       right)
+                assert rc == 0, L.anyseq_last_error()
+                for p in range(P):
+                    both = (StripPartial * 2)(left[p], right[p])
+                    res = Result()
+                    assert L.anyseq_strip_combine(C.byref(sc), both, 2, C.byref(res)) == 0
+                    assert res.score == want[p], (mode, sch, p, "chained")
+                for b in boxes:
+                    L.anyseq_strip_inbox_destroy(aligner.handle, b)
+        ref = oracle.score_affine("semiglobal", qs[1], ss[1])[0]
+        assert aligner.score("semiglobal", qs[1], ss[1], A.affine_scoring_scheme()).score == ref
+    finally:
+        aligner.tune(0, 0, 0, 10000)
+
+
 # --------------------------------------------------------------------------- tracebacks
 def test_traceback_golden_fixtures(aligner, golden):
     import anyseq_b200 as A

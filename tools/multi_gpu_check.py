@@ -37,6 +37,21 @@ wave.reset()
 p = wave.run("semiglobal", sch, d_q.data_ptr(), m, d_s.data_ptr(), c0, c1, n)
 assert wave.combine("semiglobal", sch, p).score == want
 wave.close()
+
+# (3) several alignments side by side in one launch per rank (different pairs of one shape), streamed launches
+q2, s2, _ = W.whole_genome_pair(0.06)
+q2 = q2[::-1].copy(); s2 = s2[::-1].copy()
+want2 = al.score("semiglobal", q2, s2, sch).score
+d_q2 = torch.from_numpy(q2).cuda(); d_s2 = torch.from_numpy(np.ascontiguousarray(s2[c0:c1])).cuda()
+wave = StripWavefront(al, rank, world, m, dist, depth=2, pairs_per_launch=4)
+wave.reset()
+for launch in range(3):
+    qs = [d_q.data_ptr(), d_q2.data_ptr(), d_q.data_ptr(), d_q2.data_ptr()][: 4 - launch]
+    ss = [d_s.data_ptr(), d_s2.data_ptr(), d_s.data_ptr(), d_s2.data_ptr()][: 4 - launch]
+    parts = wave.run_multi("semiglobal", sch, qs, m, ss, c0, c1, n)
+    got = [wave.combine("semiglobal", sch, p).score for p in parts]
+    assert got == [want, want2, want, want2][: 4 - launch], (launch, got, want, want2)
+wave.close()
 dist.barrier()
 if rank == 0:
     print(f"multi-GPU check ok on {world} GPUs: batch of {len(ref)} pairs, wavefront {m} x {n} score {want}")
