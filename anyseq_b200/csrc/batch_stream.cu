@@ -14,6 +14,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -73,7 +74,8 @@ public:
         next_fill_ = 0;
         kernel_ms_ = 0.f;
         launches_ = 0;
-        h2d_bytes_ = d2h_bytes_ = 0;
+        h2d_bytes_ = 0;
+        d2h_bytes_ = 0;
     }
 
     int init(int64_t cap_pairs, int64_t cap_q, int64_t cap_s, int nslots)
@@ -245,8 +247,8 @@ public:
     void stats(anyseq_result* out, long long* h2d, long long* d2h) const
     {
         if (out) { std::memset(out, 0, sizeof(*out)); out->end_i = out->end_j = -1; out->kernel_ms = kernel_ms_; out->kernel_launches = launches_; }
-        if (h2d) *h2d = h2d_bytes_;
-        if (d2h) *d2h = d2h_bytes_;
+        if (h2d) *h2d = h2d_bytes_.load();
+        if (d2h) *d2h = d2h_bytes_.load();
     }
     int64_t cap_pairs() const { return cap_pairs_; }
     int64_t cap_q() const { return cap_q_; }
@@ -265,7 +267,7 @@ private:
     int64_t cap_pairs_ = 0, cap_q_ = 0, cap_s_ = 0;
     float kernel_ms_ = 0.f;
     int launches_ = 0;
-    long long h2d_bytes_ = 0, d2h_bytes_ = 0;
+    std::atomic<long long> h2d_bytes_{0}, d2h_bytes_{0};      // producer / consumer threads
 };
 
 // ---------------------------------------------------------------------------
