@@ -34,6 +34,17 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+REF_HOST = os.path.join(_HERE, "_ref", "align_reference_host")
+
+
+def build_reference_host(reference_root: str = "/root/reference"):
+    """The reference's own host program (src/main.cpp) linked against libanyseq_b200.so; returns its path or
+    None when the reference sources are not on this machine (GPU box: the prebuilt binary travels)."""
+    if os.path.exists(os.path.join(reference_root, "src", "main.cpp")):
+        subprocess.run(["make", "-C", _HERE, "ref_host", f"REF={reference_root}"], check=True, capture_output=True)
+    return REF_HOST if os.path.exists(REF_HOST) else None
+
+
 _lib = None
 
 

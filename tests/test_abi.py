@@ -75,3 +75,22 @@ def test_product_never_touches_the_oracle():
                 assert "oracle" not in txt.lower(), os.path.join(dp, f)
     hdr = open(os.path.join(ROOT, "include", "anyseq.h")).read()
     assert "oracle" not in hdr.lower()
+
+
+def test_reference_host_program_links_against_the_library(oracle):
+    """the drop-in boundary, exercised by the reference's OWN caller: /root/reference/src/main.cpp (+ sequence_io,
+    alignment_io) compiled unmodified and linked against libanyseq_b200.so in place of the AnyDSL object code
+    (recipe: oracle/Makefile ref_host).  Needs the reference sources; on the GPU box the prebuilt binary is used."""
+    from anyseq_b200 import build
+    build.build()
+    exe = oracle.build_reference_host()
+    if exe is None:
+        pytest.skip("reference sources not on this machine and no prebuilt oracle/_ref/align_reference_host")
+    und = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
+    for sym in ("global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
+                "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment"):
+        assert sym in und, sym                      # resolved by our library at load time
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libanyseq_b200.so" in ldd and "not found" not in ldd
+    r = subprocess.run([exe], capture_output=True, text=True)     # no arguments: the reference's usage text
+    assert r.returncode == 0 and "SYNOPSIS" in r.stdout

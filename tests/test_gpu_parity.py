@@ -395,6 +395,22 @@ def test_cli_report_format():
     assert "sequence lengths: 8087, 9011" in r.stdout       # quirk Q7
 
 
+def test_reference_host_program_runs_on_the_library():
+    """the reference's unmodified main.cpp, linked against libanyseq_b200.so (oracle/Makefile ref_host), runs its
+    benchmark of all six entry points on the GPU: the drop-in boundary exercised by the reference's own caller"""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "align_reference_host")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/align_reference_host was not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-r"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "random strings with length from [256,1024]" and lines[1] == "sequence lengths: 861, 914"
+    names = ["global score", "semiglobal score", "local score", "global alignment", "semiglobal alignment", "local alignment"]
+    assert [ln.split(" ")[1:-2] for ln in lines[2:8]] == [nm.split(" ") for nm in names]
+    r = subprocess.run([exe, "-r", "10000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "sequence lengths: 8087, 9011" in r.stdout
+
+
 # --------------------------------------------------------------------------- batches
 def _pack(seqs):
     off = np.zeros(len(seqs) + 1, dtype=np.int64)
