@@ -190,3 +190,35 @@ def test_bench_reference_arm_cpu():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "GCUPS" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reader_and_printer_match_the_reference_host_code():
+    """host surface: our FASTA/FASTQ reader against the answers of the reference's OWN reader
+    (src/sequence_io.cpp:62-241, compiled where it lies by tests/golden/make_reader_golden.py) on tricky files: multi-line
+    records, CRLF (the '\\r' stays in the data), blank / comment lines, truncated FASTQ, extension vs first-character
+    sniffing, empty files, skip().  When the reference sources are present the comparison is also made live."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_reader_golden as G
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reader_golden.json")))
+    assert gold["files"] == G.FILES
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "seqio_dump_ours")
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "anyseq_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "host", "seqio_dump_ours.cpp"),
+                        os.path.join(ROOT, "anyseq_b200", "csrc", "sequence_io.cpp"), "-o", exe], check=True)
+        ours = G.run_all(exe, td)
+        assert ours == gold["expected"]
+        assert any(v["rc"] == 1 for v in ours.values()) and any("\t10\t" in v["stdout"] for v in ours.values())
+        if os.path.exists(os.path.join(G.REF, "sequence_io.cpp")):
+            assert G.run_all(G.build_ref_driver(td), td) == ours
+        # print_alignment (src/alignment_io.cpp:13-38), same scheme
+        assert gold["print_alignment_cases"] == G.ALN_CASES
+        exe = os.path.join(td, "alnio_dump_ours")
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "anyseq_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "host", "alnio_dump_ours.cpp"),
+                        os.path.join(ROOT, "anyseq_b200", "csrc", "alignment_io.cpp"), "-o", exe], check=True)
+        mine = G.run_printer(exe)
+        assert mine == gold["print_alignment"] and mine["stdout"].count("<<<") == len(G.ALN_CASES)
+        if os.path.exists(os.path.join(G.REF, "alignment_io.cpp")):
+            assert G.run_printer(G.build_ref_printer(td)) == mine
