@@ -16,6 +16,11 @@
  *     hashes recorded in SURVEY.md Appendix C (independently produced by the
  *     surveyor's model).  Linear-gap scores: pinned by (a).  Linear-space
  *     tracebacks: "restatement-pinned" (two independent restatements agree).
+ *   - What IS real reference code: the host side compiles with g++, so (i) the inputs of every Appendix C fixture are
+ *     checked against the reference's own generator (src/main.cpp included where it lies,
+ *     tests/host/refinput_dump_ref.cpp), (ii) the FASTA/FASTQ reader and print_alignment of the product are checked
+ *     against the reference's own (tests/golden/make_reader_golden.py), (iii) the reference's unmodified main.cpp runs
+ *     on the product library (oracle/Makefile ref_host).
  *   - Affine (Gotoh): the reference has only an uncalled stub
  *     (src/align.impala:153-166) => *** parity unpinned *** vs the reference;
  *     pinned only against this file's own textbook 3-state Gotoh.

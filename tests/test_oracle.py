@@ -25,6 +25,26 @@ def test_reference_rng_inputs(oracle, golden):
         assert bytes(q[:16]) == b"CGTACCAGCCGAGGTC"
 
 
+def test_reference_rng_inputs_against_the_reference_generator(golden):
+    """the same input hashes, produced by the reference's OWN generator: src/main.cpp is included where it lies (main()
+    renamed) by tests/host/refinput_dump_ref.cpp and random_string() is called with the default-seeded mt19937_64 --
+    this pins the inputs of every Appendix C fixture to real reference code, not to a restatement"""
+    import os, subprocess, tempfile
+    ref = "/root/reference/src"
+    if not os.path.exists(os.path.join(ref, "main.cpp")):
+        pytest.skip("reference sources not on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "refinput")
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++14", "-I" + ref, os.path.join(root, "tests", "host", "refinput_dump_ref.cpp"),
+                        os.path.join(ref, "sequence_io.cpp"), os.path.join(ref, "alignment_io.cpp"), "-o", exe], check=True)
+        out = subprocess.run([exe, "256", "1024", "10000", "1024", "10000", "10000"], capture_output=True, text=True, check=True).stdout
+    rows = [ln.split() for ln in out.strip().splitlines()]
+    for row, key in zip(rows, ("align -r", "align -r 10000", "align -r 10000 10000")):
+        g = golden["appendix_c"][key]
+        assert [int(row[0]), row[1], int(row[2]), row[3]] == [g["m"], g["fnv_q"], g["n"], g["fnv_s"]], key
+
+
 @pytest.mark.parametrize("key,lo,hi", [("align -r", 256, 1024), ("align -r 10000", 10000, 1024),
                                        ("align -r 10000 10000", 10000, 10000)])
 def test_appendix_c_scores(oracle, golden, key, lo, hi):
