@@ -12,7 +12,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-OUT = os.path.join(_HERE, "_build")
+OUT = os.environ.get("ANYSEQ_BUILD_DIR") or os.path.join(_HERE, "_build")   # ANYSEQ_BUILD_DIR + ANYSEQ_NVCC_FLAGS: kernel-variant experiments (anyseq_b200/_build_*/ is git-ignored)
 LIB = os.path.join(OUT, "libanyseq_b200.so")
 CLI = os.path.join(OUT, "align")
 

@@ -49,7 +49,8 @@ class StripPartial(C.Structure):
     _fields_ = [("row_best", C.c_int32), ("row_best_j", C.c_int32),
                 ("col_best", C.c_int32), ("col_best_i", C.c_int32),
                 ("local_best", C.c_int32), ("corner", C.c_int32),
-                ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32)]
+                ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32),
+                ("lenq", C.c_int32), ("lens_total", C.c_int32)]
 
 
 class BatchChunk(C.Structure):

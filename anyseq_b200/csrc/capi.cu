@@ -65,8 +65,13 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
     if (n == "cols_per_lane") t.cols_per_lane = value;
     else if (n == "band_rows") t.band_rows = value;
     else if (n == "blocks_per_sm") t.blocks_per_sm = value;
-    else if (n == "watchdog_ms") t.watchdog_ms = value;
+    else if (n == "watchdog_ms") {
+        // 0 would time every slow-path wait out, a negative value would disable the watchdog (anyseq_ctx_tune rejects both too)
+        if (value <= 0) { anyseq::set_last_error("watchdog_ms must be > 0"); return ANYSEQ_ERR_BAD_ARG; }
+        t.watchdog_ms = value;
+    }
     else if (n == "force_generic") t.force_generic = value != 0;
+    else if (n == "force_affine") t.force_affine = value != 0;
     else if (n == "local_end_cell") t.local_end_cell = value != 0;
     else if (n == "batch_chunk_bytes" && value >= (1 << 16)) t.batch_chunk_bytes = value;
     else if (n == "batch_chunk_pairs" && value >= 1) t.batch_chunk_pairs = value;
@@ -268,8 +273,12 @@ int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* p
     }
     out->kernel_ms = ms;
     out->kernel_launches = launches;
+    // end cells as finish_score_kernel reports them on one GPU (get_score_pos, src/scoring.impala:29-77)
+    const int m = parts[nranks - 1].lenq, n = parts[nranks - 1].lens_total;
     if (sc->mode == ANYSEQ_GLOBAL) {
         out->score = parts[nranks - 1].corner;
+        out->end_i = m - 1;
+        out->end_j = n - 1;
     } else if (sc->mode == ANYSEQ_SEMIGLOBAL) {
         int rs = 0, rj = -1;                       // candidate H(m-1,-1) = 0
         for (int r = 0; r < nranks; ++r)
@@ -277,8 +286,9 @@ int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* p
         int cs = 0, ci = -1;
         if (parts[nranks - 1].col_best > cs) { cs = parts[nranks - 1].col_best; ci = parts[nranks - 1].col_best_i; }
         int64_t score = rs;
+        out->end_i = m - 1;
         out->end_j = rj;
-        if (cs > rs) { score = cs; out->end_i = ci; out->end_j = -2; }
+        if (cs > rs) { score = cs; out->end_i = ci; out->end_j = n - 1; }
         out->score = score;
     } else {
         int best = anyseq::kScoreMin;

@@ -480,6 +480,8 @@ int Engine::score_device(const anyseq_scoring& sc, const uint8_t* d_q, int m, co
     anyseq_strip_partial part;
     if (m < 0 || n < 0 || !out) { set_last_error("bad lengths"); return ANYSEQ_ERR_BAD_ARG; }
     if (m == 0 || n == 0) { empty_result(sc, m, n, out); return ANYSEQ_OK; }
+    // held across the result read: h_misc_ is shared by every call on this context
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     int rc = score_strip_device(sc, d_q, m, d_s, 0, n, n, nullptr, nullptr, &part);
     if (rc) return rc;
     out->score = h_misc_[kMiscOut + 0];
@@ -500,8 +502,14 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     bool affine;
     int rc = make_score_params(sc, &sp, &affine);
     if (rc) return rc;
+    affine = affine || tune.force_affine;
     const int w = col_end - col_begin;
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
+    // the strips read / write one border record per query row of the inboxes (the next rank's lives in PEER memory)
+    if ((inbox && m > inbox->rows) || (next_inbox && m > next_inbox->rows)) {
+        set_last_error("query longer than the rows the inbox was created with");
+        return ANYSEQ_ERR_BAD_ARG;
+    }
     const bool local = sc.mode == ANYSEQ_LOCAL;
     // the end cell of a local alignment needs the whole matrix in one job (reference block grid)
     const bool track = local && (tune.local_end_cell || force_track_) && !inbox && !next_inbox && col_begin == 0 && col_end == n_total;
@@ -602,6 +610,8 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
         out->local_best = h_misc_[kMiscBest];
         out->kernel_ms = ms;
         out->kernel_launches = launches;
+        out->lenq = m;
+        out->lens_total = n_total;
     }
     return ANYSEQ_OK;
 }
@@ -624,8 +634,15 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
     bool affine;
     int rc = make_score_params(sc, &sp, &affine);
     if (rc) return rc;
+    affine = affine || tune.force_affine;
     const int w = col_end - col_begin;
     if (m < 1 || w < 1 || col_begin < 0 || col_end > n_total) { set_last_error("bad strip range"); return ANYSEQ_ERR_BAD_ARG; }
+    for (int p = 0; p < npairs; ++p) {
+        if ((inbox && inbox[p] && m > inbox[p]->rows) || (next_inbox && next_inbox[p] && m > next_inbox[p]->rows)) {
+            set_last_error("query longer than the rows the inbox was created with");
+            return ANYSEQ_ERR_BAD_ARG;
+        }
+    }
     const bool local = sc.mode == ANYSEQ_LOCAL;
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     // one alphabet for all pairs: presence bits accumulate over every sequence
@@ -728,6 +745,8 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
         out[p].local_best = h_res[(size_t)8 * npairs + p];
         out[p].kernel_ms = ms;
         out[p].kernel_launches = p == 0 ? launches : 0;
+        out[p].lenq = m;
+        out[p].lens_total = n_total;
     }
     return ANYSEQ_OK;
 }

@@ -40,6 +40,7 @@ struct Tuning {
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
     bool force_generic = false;     // never use the MASK kernels (testing)
+    bool force_affine = false;      // score path: run the Gotoh kernels even for gap_init == 0 (testing: must equal the linear kernels)
     bool local_end_cell = false;    // local scores also report the reference's end cell (single-row kernels)
     bool align_with_score = true;
     int batch_chunk_bytes = 64 << 20;    // host batches: packed symbols per pipeline chunk

@@ -36,6 +36,19 @@
 
 namespace anyseq {
 
+// Cell formulation of the multi-purpose (non-TRACK) kernels:
+//   0  "coupled":   E' = max(E+ge, X_left); H = max3(diag, E', F); X = H+go  -- 3 ALU + 3 FMA ops per Gotoh cell, but the
+//                   loop-carried chain along a row is VIADDMNMX -> VIMNMX3 -> IMAD (about 14 cycles per cell), so a warp
+//                   needs several independent rows or several co-resident warps to fill the issue slots.
+//   1  "decoupled": M = max(F+go, diag) (no horizontal input), E' = max(E+ge, M_left), X = max(E'+go, M)  -- 4 ALU + 2 FMA,
+//                   the loop-carried chain is ONE VIADDMNMX (4 cycles): valid because the E term inside H(i,j-1) can never
+//                   win the maximum that forms E(i,j) (E+go <= E+ge).  A lone warp saturates its scheduler's ALU pipe, so
+//                   half as many (twice as fast) warps are needed -- which is what the strip-to-strip chain, narrow
+//                   problems and multi-GPU slices are sensitive to.
+#ifndef ANYSEQ_CELL_FORM
+#define ANYSEQ_CELL_FORM 1
+#endif
+
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * kWarp;
 constexpr unsigned kFull = 0xffffffffu;
@@ -231,7 +244,7 @@ __device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int
 // RS / RO: the row is row RO of an RS-row group (selects its bits in the tile mask).
 // TRACK (local scheme, single-row kernels): also remember WHERE the lane's maximum was first reached, in the
 // lane's own row-major order (strict '>'), for the reference's end-cell rule (src/scoring_cpu.impala:48-72).
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C, bool TRACK = false>
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C, bool TRACK = false, int FORM = 0>
 struct Cell {
     template <int KF, int KS, int W>
     static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState<W>& s,
@@ -243,6 +256,40 @@ struct Cell {
             constexpr int BIT = (C + 1) * RS + RO;
             if constexpr (MASK) s.dd = diag_plus_sigma_mask<BIT % 32>(s.tm[BIT / 32], up, k.one, k.diff_o, k.same_o);
             else s.dd = diag_plus_sigma(s.qc, sc[C + 1], up, k.one, k.diff_o, k.same_o);
+        }
+        if constexpr (FORM == 1) {
+            // decoupled form: s.xleft carries M of the cell to the left (X of the left neighbour for the lane's first
+            // column -- both are valid second operands of E' = max(E + ge, .)), dd = X_diag + sigma (X form throughout)
+            int x;
+            if constexpr (AFFINE) {
+                const int f = __viaddmax_s32(F[C], k.ge, up);
+                int mp;
+                if constexpr (LOCAL) mp = __vimax3_s32(imad_add(f, k.one, k.go), dd, k.go);   // H >= 0  <=>  X >= go
+                else mp = __viaddmax_s32(f, k.go, dd);
+                s.e = __viaddmax_s32(s.e, k.ge, s.xleft);
+                if constexpr (PARTIAL) {
+                    if (C == k.outc) s.es = s.e;
+                }
+                x = __viaddmax_s32(s.e, k.go, mp);
+                F[C] = f;
+                s.xleft = (C + 1 < K) ? mp : x;        // the lane hands X (not M) to its right neighbour
+            } else {
+                const int nn = LOCAL ? __viaddmax_s32_relu(up, k.ge, dd) : __viaddmax_s32(up, k.ge, dd);
+                x = __viaddmax_s32(s.xleft, k.ge, nn);
+                s.xleft = x;
+            }
+            if constexpr (LOCAL) {
+                if constexpr (PARTIAL) {
+                    if (C < k.nvalid) s.best = max(s.best, x);
+                } else if constexpr ((C & 1) != 0) {
+                    s.best = __vimax3_s32(s.best, s.hprev, x);
+                } else {
+                    s.hprev = x;
+                }
+            }
+            X[C] = x;
+            if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK, FORM>::run(X, F, sc, s, k);
+            return;
         }
         int h;
         if constexpr (AFFINE) {
@@ -271,7 +318,7 @@ struct Cell {
         const int x = AFFINE ? imad_add(h, k.one, k.go) : h;
         X[C] = x;
         s.xleft = x;
-        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK>::run(X, F, sc, s, k);
+        if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK, FORM>::run(X, F, sc, s, k);
     }
 };
 
@@ -292,7 +339,7 @@ struct StepStateR {
     int xs[R], es[R];    // PARTIAL: X and E of the edge column, per row
 };
 
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, int C>
+template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, int C, int FORM = 0>
 struct CellR {
     template <int KF, int KS, int W>
     static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepStateR<R, W>& s,
@@ -311,7 +358,28 @@ struct CellR {
                 else s.dd[r] = diag_plus_sigma(s.qc[r], sc[C + 1], above_x, k.one, k.diff_o, k.same_o);
             }
             int h, x;
-            if constexpr (AFFINE) {
+            if constexpr (FORM == 1 && AFFINE) {
+                // decoupled form (see Cell): s.x[r] carries M of the cell to the left, hrow holds X (= H + go)
+                const int f = __viaddmax_s32(above_f, k.ge, above_x);
+                int mp;
+                if constexpr (LOCAL) mp = __vimax3_s32(imad_add(f, k.one, k.go), dd, k.go);
+                else mp = __viaddmax_s32(f, k.go, dd);
+                s.e[r] = __viaddmax_s32(s.e[r], k.ge, s.x[r]);
+                x = __viaddmax_s32(s.e[r], k.go, mp);
+                h = x;
+                above_f = f;
+                hrow[r] = h;
+                s.x[r] = (C + 1 < K) ? mp : x;
+                above_x = x;
+                if constexpr (PARTIAL) {
+                    if (C == k.outc) { s.xs[r] = x; s.es[r] = s.e[r]; }
+                }
+                continue;
+            } else if constexpr (FORM == 1) {
+                const int nn = LOCAL ? __viaddmax_s32_relu(above_x, k.ge, dd) : __viaddmax_s32(above_x, k.ge, dd);
+                h = __viaddmax_s32(s.x[r], k.ge, nn);
+                x = h;
+            } else if constexpr (AFFINE) {
                 s.e[r] = __viaddmax_s32(s.e[r], k.ge, s.x[r]);
                 const int f = __viaddmax_s32(above_f, k.ge, above_x);
                 h = LOCAL ? __vimax3_s32_relu(dd, s.e[r], f) : __vimax3_s32(dd, s.e[r], f);
@@ -342,7 +410,7 @@ struct CellR {
         }
         X[C] = above_x;
         if constexpr (AFFINE) F[C] = above_f;
-        if constexpr (C + 1 < K) CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, C + 1>::run(X, F, sc, s, k);
+        if constexpr (C + 1 < K) CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, C + 1, FORM>::run(X, F, sc, s, k);
     }
 };
 
@@ -386,6 +454,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     constexpr int B = 32 / R;              // steps per batch (a batch = 32 rows)
     constexpr int QM = 64 * R - 1;         // query ring mask
     constexpr int W = TileWords<R, K>::value;
+    constexpr int FORM = TRACK ? 0 : ANYSEQ_CELL_FORM;     // the end-cell tracking kernels keep the coupled form (they need H itself)
     const int i0 = band * J.band_h;
     const int hb = min(J.band_h, J.h - i0);
     const int j0 = strip * SW;
@@ -396,8 +465,9 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     k.one = a.one;
     k.ge = a.sp.gap_extend;
     k.go = go;
-    k.diff_o = a.sp.diff - go;
-    k.same_o = a.sp.same - go;
+    // coupled form: dd = H_diag + sigma = X_diag + (sigma - go); decoupled form: dd = X_diag + sigma
+    k.diff_o = FORM == 1 ? a.sp.diff : a.sp.diff - go;
+    k.same_o = FORM == 1 ? a.sp.same : a.sp.same - go;
     int* const status = a.status;
     const unsigned long long timeout_ns = a.timeout_ns;
 
@@ -531,7 +601,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         dcarry = xl;
         st.xleft = xl;
         st.e = el;
-        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK>::run(X, F, sc, st, k);
+        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK, FORM>::run(X, F, sc, st, k);
         hro = st.xleft;
         ero = st.e;
         if constexpr (PARTIAL) {
@@ -596,7 +666,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             dcarry = xl[R - 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) { s2.xs[r] = 0; s2.es[r] = 0; }
-            CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, 0>::run(X, F, sc, s2, k);
+            CellR<LOCAL, AFFINE, K, PARTIAL, MASK, R, 0, FORM>::run(X, F, sc, s2, k);
 #pragma unroll
             for (int r = 0; r < R; ++r) { hr[r] = s2.x[r]; er[r] = s2.e[r]; }
             st.best = s2.best;
@@ -742,6 +812,9 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         if constexpr (!PARTIAL) best = max(best, st.hprev);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
+        if constexpr (FORM == 1 && AFFINE) {
+            if (best > kScoreMin) best -= go;             // the decoupled Gotoh cells track X = H + go
+        }
         if (lane == 0) atomicMax(J.best, best);
     }
     // band hand-over: bottom border + corner are visible before the row counter

@@ -241,6 +241,7 @@ typedef struct anyseq_strip_partial {
     int32_t corner;                    /* last rank: H(m-1, n-1) */
     float   kernel_ms;
     int32_t kernel_launches;
+    int32_t lenq, lens_total;          /* the whole matrix (filled by the engine): combine reports end cells like a single-GPU run */
 } anyseq_strip_partial;
 int anyseq_score_strip_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                               const void* d_query, int lenq,

@@ -26,7 +26,7 @@ class _Result(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so with the committed Makefile (gcc/g++ only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("anyseq_oracle.c", "anyseq_oracle.h", "refinput.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("anyseq_oracle.c", "anyseq_oracle.h", "refinput.cpp", "fullsize_check.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -63,6 +63,8 @@ def lib():
     L.oracle_score_affine.restype = _Result
     L.oracle_score_affine.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fullsize_score.restype = _Result
+    L.fullsize_score.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.textbook_score_linear.restype = C.c_int32
     L.textbook_score_linear.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.textbook_score_affine.restype = C.c_int32
@@ -126,6 +128,15 @@ def score_affine(mode, q, s, same=2, diff=-1, gap_init=-2, gap_extend=-1, thread
     q, s = _u8(q), _u8(s)
     r = lib().oracle_score_affine(_mode(mode), _ptr(q), len(q), _ptr(s), len(s),
                                   same, diff, gap_init, gap_extend, threads, block_w, block_h)
+    return r.score, r.pos_i, r.pos_j
+
+
+def fullsize_score(mode, q, s, same=2, diff=-1, gap_init=-2, gap_extend=-1, threads=4):
+    """(score, pos_i, pos_j) of the vectorised second CPU implementation (oracle/fullsize_check.c): the same
+    recurrences and result extraction as score_affine / score_linear (gap_init = 0), fast enough for 4.6 Mbp^2.
+    Local: score only (pos = -1)."""
+    q, s = _u8(q), _u8(s)
+    r = lib().fullsize_score(_mode(mode), _ptr(q), len(q), _ptr(s), len(s), same, diff, gap_init, gap_extend, threads)
     return r.score, r.pos_i, r.pos_j
 
 

@@ -43,11 +43,16 @@ def test_sass_is_sm100a_with_dpx():
     from anyseq_b200 import capi
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq12strip_kernelILb0ELb1ELi32EEEvNS_10KernelArgsE",
-                           capi.LIB_PATH], capture_output=True, text=True).stdout
-    if "VIADDMNMX" not in sass:     # older cuobjdump: fall back to a whole-file dump
-        sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "VIADDMNMX" in sass and "VIMNMX3" in sass and "IMAD" in sass
+    # the headline kernel: strip_kernel<LOCAL=0, AFFINE=1, K=32, MASK=1, TRACK=0> (five template arguments)
+    hot = "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0EEEvNS_10KernelArgsE"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", hot, capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "Function : " + hot in sass, "hot kernel not found in the library (mangled name changed?)"
+    n_dpx = sass.count("VIADDMNMX") + sass.count("VIMNMX3")
+    assert n_dpx >= 500 and sass.count("IMAD") >= 500 and "R2P" in sass, (n_dpx, sass.count("IMAD"))
+    # the local and the linear-gap kernels use the .RELU / two-operand forms
+    loc = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq12strip_kernelILb1ELb0ELi32ELb1ELb0EEEvNS_10KernelArgsE",
+                          capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "VIADDMNMX.RELU" in loc
     # packed batch kernels: two 16-bit cells per DPX instruction, predicates from R2P
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq15batch_x2_kernelILi1ELb1ELi16EEEvNS_9BatchArgsE",
                            capi.LIB_PATH], capture_output=True, text=True).stdout

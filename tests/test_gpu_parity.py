@@ -213,8 +213,57 @@ def test_large_properties(aligner):
         assert aligner.score("global", t, q, sch).score == g
         assert aligner.score("semiglobal", t, q, sch).score == sg
         assert aligner.score("local", t, q, sch).score == lo
-    # gi = 0 Gotoh == linear, via two different kernels
-    assert aligner.score("global", q, t, A.affine_scoring_scheme(2, -1, -1, 0)).score <= g + 1 or True
+    # gi = 0 Gotoh == linear, via two different kernels: force_affine runs the Gotoh cells with go == ge
+    for mode in MODES:
+        want = aligner.score(mode, q, t, lin)
+        aligner.set_option("force_affine", 1)
+        try:
+            got = aligner.score(mode, q, t, A.affine_scoring_scheme(2, -1, 0, -1))
+        finally:
+            aligner.set_option("force_affine", 0)
+        assert (got.score, got.end_i, got.end_j) == (want.score, want.end_i, want.end_j), mode
+
+
+def test_large_mismatch_rich_all_strip_widths(aligner):
+    """600 kbp, mismatch- and indel-rich (scores far from the identity line, E/F alive everywhere): every strip width,
+    the generic (byte-compare) kernels and several CTA counts must give the same score and end cell -- an inter-strip
+    race or a lost border record would show up as a difference between decompositions"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(4242)
+    n = 600_000
+    q = _rand(rng, n)
+    t = _related(rng, q, n - 7_777, sub=0.25)
+    sch = A.affine_scoring_scheme(2, -1, -2, -1)
+    for mode in MODES:
+        ref = None
+        for (K, bps, generic) in ((8, 0, 0), (16, 0, 0), (32, 0, 0), (16, 1, 0), (32, 1, 0), (16, 0, 1), (4, 0, 0)):
+            aligner.tune(cols_per_lane=K, blocks_per_sm=bps)
+            aligner.set_option("force_generic", generic)
+            try:
+                r = aligner.score(mode, q, t, sch)
+            finally:
+                aligner.set_option("force_generic", 0)
+                aligner.tune()
+            got = (r.score, r.end_i, r.end_j)
+            if ref is None:
+                ref = got
+            assert got == ref, (mode, K, bps, generic, got, ref)
+
+
+def test_full_size_c2_against_cpu(aligner):
+    """BASELINE.json configs[1] at its stated size against the frozen CPU result (tests/golden/fullsize.json, produced by
+    tools/freeze_fullsize.py with oracle/fullsize_check.c): score AND end cell of the 4.64 Mbp x 4.6 Mbp semiglobal Gotoh run"""
+    import json
+    import anyseq_b200 as A
+    from anyseq_b200 import workloads as W
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")
+    gold = json.load(open(path)).get("c2_semiglobal_affine")
+    if gold is None:
+        pytest.skip("tests/golden/fullsize.json has no full-size C2 entry yet")
+    q, s, _ = W.whole_genome_pair(1.0)
+    assert (len(q), len(s)) == (gold["m"], gold["n"])
+    r = aligner.score("semiglobal", q, s, A.affine_scoring_scheme(*gold["scheme"]))
+    assert (r.score, r.end_i, r.end_j) == (gold["score"], gold["end_i"], gold["end_j"])
 
 
 def test_full_size_identity(aligner):
@@ -256,8 +305,42 @@ def test_split_ranks_equal_single_run(aligner, oracle):
                 assert L.anyseq_strip_combine(C.byref(sc), parts, 2, C.byref(res)) == 0
                 L.anyseq_strip_inbox_destroy(aligner.handle, box)
                 ref = (oracle.score_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend) if sch.affine
-                       else oracle.score_linear(mode, q, s, sch.same, sch.diff, sch.gap_extend))[0]
-                assert res.score == ref == aligner.score(mode, q, s, sch).score, (mode, sch, cut)
+                       else oracle.score_linear(mode, q, s, sch.same, sch.diff, sch.gap_extend))
+                one = aligner.score(mode, q, s, sch)
+                assert res.score == ref[0] == one.score, (mode, sch, cut)
+                # end cells of the combined ranks == single-GPU run (== get_score_pos of the restated reference)
+                assert (res.end_i, res.end_j) == (one.end_i, one.end_j), (mode, sch, cut)
+                if mode != "local":
+                    assert (res.end_i, res.end_j) == ref[1:], (mode, sch, cut)
+
+
+def test_inbox_shorter_than_the_query_is_refused(aligner):
+    """an inbox holds one border record per query row; a longer query would make the last strip write past the end of
+    the NEXT rank's (peer) memory -- the call must fail with ANYSEQ_ERR_BAD_ARG instead"""
+    from anyseq_b200 import capi
+    from anyseq_b200.capi import StripPartial, make_scoring
+    import torch
+    L = capi.load_library()
+    rng = np.random.default_rng(3)
+    q = _rand(rng, 3000); s = _rand(rng, 4000)
+    dq = torch.from_numpy(q).cuda(); ds = torch.from_numpy(s).cuda()
+    sc = make_scoring("semiglobal", 2, -1, -2, -1)
+    box = C.c_void_p()
+    assert L.anyseq_strip_inbox_create(aligner.handle, 2999, C.byref(box), None) == 0
+    part = StripPartial()
+    vp = C.c_void_p
+    rc = L.anyseq_score_strip_device(aligner.handle, C.byref(sc), vp(dq.data_ptr()), len(q), vp(ds.data_ptr()), 0, 2048,
+                                     len(s), None, box, C.byref(part))
+    assert rc == -2 and b"inbox" in L.anyseq_last_error()
+    rc = L.anyseq_score_strip_device(aligner.handle, C.byref(sc), vp(dq.data_ptr()), len(q), vp(ds.data_ptr() + 2048), 2048,
+                                     len(s), len(s), box, None, C.byref(part))
+    assert rc == -2
+    qp = (vp * 2)(dq.data_ptr(), dq.data_ptr()); sp = (vp * 2)(ds.data_ptr(), ds.data_ptr())
+    boxes = (vp * 2)(box, box)
+    parts = (StripPartial * 2)()
+    rc = L.anyseq_score_strip_device_multi(aligner.handle, C.byref(sc), 2, qp, len(q), sp, 0, 2048, len(s), None, boxes, parts)
+    assert rc == -2
+    L.anyseq_strip_inbox_destroy(aligner.handle, box)
 
 
 def test_multi_pair_launch_equals_single_runs(aligner, oracle):

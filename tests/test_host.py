@@ -65,6 +65,7 @@ part.row_best = int(row.max()); part.row_best_j = int(c0 + int(np.argmax(row)))
 col = H[1:, c1]
 part.col_best = int(col.max()); part.col_best_i = int(np.argmax(col))
 part.local_best = 0; part.corner = int(H[m, c1]); part.kernel_ms = 1.0; part.kernel_launches = 3
+part.lenq = m; part.lens_total = n
 parts = [None] * world
 dist.all_gather_object(parts, bytes(part))
 arr = (StripPartial * world)(*[StripPartial.from_buffer_copy(p) for p in parts])
@@ -72,8 +73,8 @@ L = capi.load_library()
 sc = make_scoring("semiglobal", 2, -1, 0, -1)
 res = Result()
 assert L.anyseq_strip_combine(C.byref(sc), arr, world, C.byref(res)) == 0
-want = O.score_linear("semiglobal", q, s)[0]
-assert res.score == want, (res.score, want)
+want = O.score_linear("semiglobal", q, s)
+assert (res.score, res.end_i, res.end_j) == want, ((res.score, res.end_i, res.end_j), want)   # end cell as on one GPU
 assert res.kernel_launches == 3 * world
 dist.destroy_process_group()
 print("rank", rank, "ok", res.score)

@@ -234,3 +234,35 @@ def test_affine_traceback_is_optimal_global(oracle):
             assert ret == gi + m * ge
             etypes += int(ty.sum())
     assert etypes > 0
+
+
+def test_fullsize_check_equals_oracle(oracle):
+    """oracle/fullsize_check.c (the vectorised second CPU implementation that freezes the full-size C2 result,
+    tools/freeze_fullsize.py) against the scalar restatement: scores and end cells, all schemes, ragged shapes around
+    its 2048 x 512 tiles, sequences with long gaps and non-ACGT bytes"""
+    rng = np.random.default_rng(99)
+    shapes = [(1, 1), (3, 2047), (511, 2048), (513, 2049), (700, 4097), (2500, 6000), (5000, 300), (1025, 10241)]
+    for (m, n) in shapes:
+        a = _rand(rng, m)
+        b = _rand(rng, n)
+        if m > 400:                      # related sequences with a long gap: E and F chains cross tile borders
+            b = np.concatenate([a[: m // 2], _rand(rng, 300), a[m // 2:], b])[:n]
+        for mode in MODES:
+            for (gi, ge) in ((-2, -1), (0, -1), (-7, -3)):
+                got = oracle.fullsize_score(mode, a, b, 2, -1, gi, ge, threads=3)
+                want = oracle.score_affine(mode, a, b, 2, -1, gi, ge) if gi else oracle.score_linear(mode, a, b, 2, -1, ge)
+                assert got[0] == want[0], (m, n, mode, gi, ge)
+                if mode != "local":
+                    assert got == want, (m, n, mode, gi, ge)
+    raw = rng.integers(0, 256, 3000).astype(np.uint8)
+    raw2 = np.concatenate([raw[100:2000], rng.integers(0, 256, 900).astype(np.uint8)])
+    for mode in MODES:
+        assert oracle.fullsize_score(mode, raw, raw2, 3, -2, -4, -1)[0] == oracle.score_affine(mode, raw, raw2, 3, -2, -4, -1)[0]
+    # the frozen scaled-down C2 entry is reproduced by the scalar restatement
+    import json, os
+    from anyseq_b200 import workloads as W
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")))
+    g = gold["c2_semiglobal_affine_scale_0.02"]
+    q, s, _ = W.whole_genome_pair(0.02)
+    assert "%016x" % oracle.fnv1a64(q) == g["fnv_q"] and "%016x" % oracle.fnv1a64(s) == g["fnv_s"]
+    assert oracle.score_affine("semiglobal", q, s, threads=8) == (g["score"], g["end_i"], g["end_j"])
