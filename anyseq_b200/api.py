@@ -201,6 +201,18 @@ class Aligner:
                                                         C.byref(res)))
         return AlignmentResult(res.score, -1, -1, res.kernel_ms, res.kernel_launches)
 
+    # -- 2-bit packed DNA batches (anyseq_score_batch_packed2) -----------------
+    def score_batch_packed2(self, mode, batch: "capi.PackedBatch", scores, scoring: ScoringScheme = REFERENCE_SCORING,
+                            device: bool = False) -> AlignmentResult:
+        """batch: capi.PackedBatch with host addresses (device=False: chunks are copied from the caller's memory under
+        the kernels; pin the arrays for full H2D speed) or device addresses (device=True); scores: address of npairs
+        int32 (host resp. device)"""
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        res = Result()
+        fn = self._lib.anyseq_score_batch_packed2_device if device else self._lib.anyseq_score_batch_packed2
+        self._check(fn(self._ctx, C.byref(sc), C.byref(batch), C.c_void_p(int(scores)), C.byref(res)))
+        return AlignmentResult(res.score, -1, -1, res.kernel_ms, res.kernel_launches)
+
     def batch_stream(self, mode, scoring: ScoringScheme = REFERENCE_SCORING, cap_pairs: int = 1 << 17,
                      cap_query_bytes: int = 32 << 20, cap_subject_bytes: int = 32 << 20, slots: int = 3) -> "BatchStream":
         return BatchStream(self, mode, scoring, cap_pairs, cap_query_bytes, cap_subject_bytes, slots)
@@ -210,6 +222,28 @@ class Aligner:
         ops, mhz = C.c_double(), C.c_float()
         self._check(self._lib.anyseq_measure_int_peak(self._ctx, kind, C.byref(ops), C.byref(mhz)))
         return ops.value, mhz.value
+
+
+def pack2(seqs: np.ndarray) -> np.ndarray:
+    """(npairs, L) uint8 array of A/C/G/T (either case) -> (npairs, ceil(L/4)) packed bytes: four symbols per byte, least
+    significant bits first, every row starting on a byte boundary (the layout anyseq_score_batch_packed2 reads with
+    stride = ceil(L/4)).  Vectorised equivalent of the C helper anyseq_pack2."""
+    a = np.ascontiguousarray(seqs, dtype=np.uint8)
+    if a.ndim == 1:
+        a = a[None, :]
+    lut = np.full(256, 255, dtype=np.uint8)
+    for k, ch in enumerate(b"ACGT"):
+        lut[ch] = k
+        lut[ch + 32] = k
+    codes = lut[a]
+    if (codes == 255).any():
+        raise ValueError("pack2: only A/C/G/T can be packed")
+    L = a.shape[1]
+    pad = (-L) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros((a.shape[0], pad), dtype=np.uint8)], axis=1)
+    c = codes.reshape(a.shape[0], -1, 4)
+    return np.ascontiguousarray(c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6))
 
 
 class BatchStream:

@@ -16,7 +16,7 @@ OUT = os.environ.get("ANYSEQ_BUILD_DIR") or os.path.join(_HERE, "_build")   # AN
 LIB = os.path.join(OUT, "libanyseq_b200.so")
 CLI = os.path.join(OUT, "align")
 
-LIB_SOURCES = ["engine.cu", "capi.cu", "microbench.cu", "inbox.cu", "traceback.cu", "traceback_affine.cu", "traceback_full.cu", "batch.cu", "batch_x2.cu", "batch_stream.cu",
+LIB_SOURCES = ["engine.cu", "capi.cu", "microbench.cu", "inbox.cu", "traceback.cu", "traceback_affine.cu", "traceback_full.cu", "batch.cu", "batch_x2.cu", "batch_stream.cu", "batch_packed2.cu",
                "strip_inst_00.cu", "strip_inst_01.cu", "strip_inst_10.cu", "strip_inst_11.cu",
                "strip_inst_10t.cu", "strip_inst_11t.cu"]
 CLI_SOURCES = ["align_main.cpp", "sequence_io.cpp", "alignment_io.cpp"]

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
     "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_last_split_types", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
+    "anyseq_score_batch_packed2", "anyseq_score_batch_packed2_device", "anyseq_pack2",
     "anyseq_batch_stream_open", "anyseq_batch_stream_acquire", "anyseq_batch_stream_submit", "anyseq_batch_stream_finish",
     "anyseq_batch_stream_collect", "anyseq_batch_stream_release", "anyseq_batch_stream_stats", "anyseq_batch_stream_close",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
@@ -51,6 +52,14 @@ class StripPartial(C.Structure):
                 ("local_best", C.c_int32), ("corner", C.c_int32),
                 ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32),
                 ("lenq", C.c_int32), ("lens_total", C.c_int32)]
+
+
+class PackedBatch(C.Structure):
+    """anyseq_packed_batch: 2-bit packed DNA batch (host or device pointers as plain addresses)"""
+    _fields_ = [("q2", C.c_void_p), ("s2", C.c_void_p), ("q_boff", C.c_void_p), ("s_boff", C.c_void_p),
+                ("q_len", C.c_void_p), ("s_len", C.c_void_p),
+                ("q_len_uniform", C.c_int32), ("s_len_uniform", C.c_int32),
+                ("q_stride", C.c_int64), ("s_stride", C.c_int64), ("npairs", C.c_int64)]
 
 
 class BatchChunk(C.Structure):
@@ -122,6 +131,12 @@ def load_library(path: str | None = None):
                                      C.POINTER(C.c_int32), C.POINTER(Result)]
     L.anyseq_score_batch_device.restype = C.c_int
     L.anyseq_score_batch_device.argtypes = [vp, C.POINTER(Scoring), vp, vp, vp, vp, C.c_int64, vp, C.POINTER(Result)]
+    L.anyseq_score_batch_packed2.restype = C.c_int
+    L.anyseq_score_batch_packed2.argtypes = [vp, C.POINTER(Scoring), C.POINTER(PackedBatch), vp, C.POINTER(Result)]
+    L.anyseq_score_batch_packed2_device.restype = C.c_int
+    L.anyseq_score_batch_packed2_device.argtypes = [vp, C.POINTER(Scoring), C.POINTER(PackedBatch), vp, C.POINTER(Result)]
+    L.anyseq_pack2.restype = C.c_int64
+    L.anyseq_pack2.argtypes = [vp, C.c_int64, vp]
     L.anyseq_batch_stream_open.restype = C.c_int
     L.anyseq_batch_stream_open.argtypes = [vp, C.POINTER(Scoring), C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp)]
     for name in ("acquire", "submit", "collect", "release"):

@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
     extern __shared__ unsigned s_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if constexpr (MASK) {
-        for (int x = threadIdx.x; x < 256; x += kThreads) s_lut[x] = a.lut[x];
+        if (!a.packed2) {
+            for (int x = threadIdx.x; x < 256; x += kThreads) s_lut[x] = a.lut[x];
+        }
         __syncthreads();
     }
     unsigned* s_mask = s_dyn + warp * a.ncodes * 32;
@@ -83,8 +85,8 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
 
     long long pair = (long long)blockIdx.x * kWarpsPerBlock + warp;
     while (pair < a.npairs) {
-        const long long q0 = a.qoff[pair], s0 = a.soff[pair];
-        const int lq = (int)(a.qoff[pair + 1] - q0), ls = (int)(a.soff[pair + 1] - s0);
+        const long long q0 = batch_q_start(a, pair), s0 = batch_s_start(a, pair);
+        const int lq = batch_q_len(a, pair), ls = batch_s_len(a, pair);
         int score;
         if (lq == 0 || ls == 0) {
             // quirk Q12 (see engine.cu: empty_result)
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
 #pragma unroll 4
                 for (int c = 0; c < K; ++c) {
                     const int j = jl + c;
-                    const int cd = (j < n) ? (int)s_lut[cols[j]] : 0;
+                    const int cd = (j < n) ? batch_code(cols, j, a.packed2, s_lut) : 0;
                     if (cd) s_mask[cd * 32 + lane] |= 1u << c;
                 }
                 __syncwarp();
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                 {
                     const int r = tb + lane;
                     uint8_t v = 0;
-                    if (r < m) v = MASK ? s_lut[rows[r]] : rows[r];
+                    if (r < m) v = MASK ? (uint8_t)batch_code(rows, r, a.packed2, s_lut) : rows[r];
                     rq[r & 63] = v;
                     __syncwarp();
                     if constexpr (MASK) st.tm[0] = row_mask(tb - lane);
@@ -225,37 +227,12 @@ static BatchKernelFn pick_batch_kernel(int mode, bool affine, int K, bool mask)
     }
 }
 
-int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, const int64_t* d_qoff,
-                               const uint8_t* d_s, const int64_t* d_soff, int64_t npairs, int32_t* d_scores,
-                               anyseq_result* out)
+// Chooses the batch kernel for pairs of at most (max_long, max_short) symbols (alphabet already analysed: use_mask_,
+// ncodes_) and launches it on `st`; ba carries the input description and the score array.
+int Engine::launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool affine, BatchArgs& ba, int max_long,
+                         int max_short, cudaStream_t st)
 {
-    std::lock_guard<std::recursive_mutex> lock(mu_);
-    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
-    ScoreParams sp;
-    bool affine;
-    int rc = make_score_params(sc, &sp, &affine);
-    if (rc) return rc;
-    if (out) { std::memset(out, 0, sizeof(*out)); out->end_i = out->end_j = -1; }
-    if (npairs == 0) return ANYSEQ_OK;
-    if (sc.mode == ANYSEQ_LOCAL && sc.diff > 0) {
-        set_last_error("batch local alignment needs diff <= 0 (padded columns must not outscore real ones)");
-        return ANYSEQ_ERR_UNSUPPORTED;
-    }
-    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    // totals (for the alphabet scan) and length statistics
-    long long tot[2] = {0, 0};
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(&tot[0], d_qoff + npairs, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(&tot[1], d_soff + npairs, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
-    int* d_stats = misc_.as<int>() + kMiscOut;
-    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(int) * 2, stream_));
-    batch_stats_kernel<<<(int)std::min<long long>(sm_count * 8, (npairs + 255) / 256), 256, 0, stream_>>>(
-        reinterpret_cast<const long long*>(d_qoff), reinterpret_cast<const long long*>(d_soff), npairs, d_stats);
-    ANYSEQ_CUDA_CHECK(cudaGetLastError());
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_ + kMiscOut, d_stats, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream_));
-    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    const int max_long = h_misc_[kMiscOut], max_short = h_misc_[kMiscOut + 1];
-    rc = analyse_alphabet(d_q, tot[0], d_s, tot[1]);
-    if (rc) return rc;
+    const long long npairs = ba.npairs;
     const int limit = use_mask_ ? 1024 : 512;
     int cols_longer, ncols;
     if (max_long <= limit) { cols_longer = 1; ncols = max_long; }
@@ -292,13 +269,6 @@ int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, con
     if (nb < 1) { set_last_error("batch kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     const long long units = packed ? (npairs + 1) / 2 : npairs;      // work items claimed by the warps
     const int grid = (int)std::min<long long>((long long)nb * sm_count, (units + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    BatchArgs ba;
-    ba.q = d_q;
-    ba.qoff = reinterpret_cast<const long long*>(d_qoff);
-    ba.s = d_s;
-    ba.soff = reinterpret_cast<const long long*>(d_soff);
-    ba.npairs = npairs;
-    ba.scores = d_scores;
     ba.sp = sp;
     ba.gap_init = sc.gap_init;
     ba.mode = sc.mode;
@@ -309,9 +279,53 @@ int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, con
     ba.lut = lut_.as<uint8_t>();
     ba.counter = reinterpret_cast<unsigned long long*>(misc_.as<int>() + kMiscCounter);
     const unsigned long long first = (unsigned long long)grid * kWarpsPerBlock;
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ba.counter, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
-    fn<<<grid, kThreads, dyn, stream_>>>(ba);
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ba.counter, &first, sizeof(first), cudaMemcpyHostToDevice, st));
+    fn<<<grid, kThreads, dyn, st>>>(ba);
     ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    return ANYSEQ_OK;
+}
+
+int Engine::score_batch_device(const anyseq_scoring& sc, const uint8_t* d_q, const int64_t* d_qoff,
+                               const uint8_t* d_s, const int64_t* d_soff, int64_t npairs, int32_t* d_scores,
+                               anyseq_result* out)
+{
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
+    ScoreParams sp;
+    bool affine;
+    int rc = make_score_params(sc, &sp, &affine);
+    if (rc) return rc;
+    if (out) { std::memset(out, 0, sizeof(*out)); out->end_i = out->end_j = -1; }
+    if (npairs == 0) return ANYSEQ_OK;
+    if (sc.mode == ANYSEQ_LOCAL && sc.diff > 0) {
+        set_last_error("batch local alignment needs diff <= 0 (padded columns must not outscore real ones)");
+        return ANYSEQ_ERR_UNSUPPORTED;
+    }
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    // totals (for the alphabet scan) and length statistics
+    long long tot[2] = {0, 0};
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(&tot[0], d_qoff + npairs, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(&tot[1], d_soff + npairs, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    int* d_stats = misc_.as<int>() + kMiscOut;
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(int) * 2, stream_));
+    batch_stats_kernel<<<(int)std::min<long long>(sm_count * 8, (npairs + 255) / 256), 256, 0, stream_>>>(
+        reinterpret_cast<const long long*>(d_qoff), reinterpret_cast<const long long*>(d_soff), npairs, d_stats);
+    ANYSEQ_CUDA_CHECK(cudaGetLastError());
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(h_misc_ + kMiscOut, d_stats, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream_));
+    ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    const int max_long = h_misc_[kMiscOut], max_short = h_misc_[kMiscOut + 1];
+    rc = analyse_alphabet(d_q, tot[0], d_s, tot[1]);
+    if (rc) return rc;
+    BatchArgs ba;
+    std::memset(&ba, 0, sizeof(ba));
+    ba.q = d_q;
+    ba.qoff = reinterpret_cast<const long long*>(d_qoff);
+    ba.s = d_s;
+    ba.soff = reinterpret_cast<const long long*>(d_soff);
+    ba.npairs = npairs;
+    ba.scores = d_scores;
+    rc = launch_batch(sc, sp, affine, ba, max_long, max_short, stream_);
+    if (rc) return rc;
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
     float ms = 0.f;

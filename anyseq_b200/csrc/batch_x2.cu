@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
     __shared__ uint8_t s_lut[256];
     extern __shared__ unsigned s_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int x = threadIdx.x; x < 256; x += kThreads) s_lut[x] = a.lut[x];
+    if (!a.packed2) {
+        for (int x = threadIdx.x; x < 256; x += kThreads) s_lut[x] = a.lut[x];
+    }
     __syncthreads();
     constexpr int W = (2 * K + 31) / 32;              // words of match bits per lane and row
     unsigned* maskA = s_dyn + (warp * 2 + 0) * a.ncodes * 32 * W;     // [code][lane][W], bits 2c
@@ -144,15 +146,15 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
     long long pp = (long long)blockIdx.x * kWarpsPerBlock + warp;
     while (pp < npp) {
         const long long pA = 2 * pp, pB = min(2 * pp + 1, a.npairs - 1);
-        const int lqA = (int)(a.qoff[pA + 1] - a.qoff[pA]), lsA = (int)(a.soff[pA + 1] - a.soff[pA]);
-        const int lqB = (int)(a.qoff[pB + 1] - a.qoff[pB]), lsB = (int)(a.soff[pB + 1] - a.soff[pB]);
+        const int lqA = batch_q_len(a, pA), lsA = batch_s_len(a, pA);
+        const int lqB = batch_q_len(a, pB), lsB = batch_s_len(a, pB);
         const bool same_shape = lqA == lqB && lsA == lsB;
         const int npass = same_shape ? 1 : 2;
         for (int pass = 0; pass < npass; ++pass) {
             const long long pa = (same_shape || pass == 0) ? pA : pB;
             const long long pb = same_shape ? pB : pa;
-            const long long qa0 = a.qoff[pa], sa0 = a.soff[pa], qb0 = a.qoff[pb], sb0 = a.soff[pb];
-            const int lq = (int)(a.qoff[pa + 1] - qa0), ls = (int)(a.soff[pa + 1] - sa0);
+            const long long qa0 = batch_q_start(a, pa), sa0 = batch_s_start(a, pa), qb0 = batch_q_start(a, pb), sb0 = batch_s_start(a, pb);
+            const int lq = batch_q_len(a, pa), ls = batch_s_len(a, pa);
             int scoreA, scoreB;
             if (lq == 0 || ls == 0) {
                 // quirk Q12 (see engine.cu: empty_result)
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
 #pragma unroll 4
                 for (int c = 0; c < K; ++c) {
                     const int j = jl + c;
-                    const int ca = (j < n) ? (int)s_lut[colsA[j]] : 0;
-                    const int cb = (j < n) ? (int)s_lut[colsB[j]] : 0;
+                    const int ca = (j < n) ? batch_code(colsA, j, a.packed2, s_lut) : 0;
+                    const int cb = (j < n) ? batch_code(colsB, j, a.packed2, s_lut) : 0;
                     if (ca) maskA[(ca * 32 + lane) * W + (2 * c) / 32] |= 1u << ((2 * c) % 32);
                     if (cb) maskB[(cb * 32 + lane) * W + (2 * c) / 32] |= 2u << ((2 * c) % 32);
                 }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
                     {
                         const int r = tb + lane;
                         uint8_t va = 0, vb = 0;
-                        if (r < m) { va = s_lut[rowsA[r]]; vb = s_lut[rowsB[r]]; }
+                        if (r < m) { va = (uint8_t)batch_code(rowsA, r, a.packed2, s_lut); vb = (uint8_t)batch_code(rowsB, r, a.packed2, s_lut); }
                         rqA[r & 63] = va;
                         rqB[r & 63] = vb;
                         __syncwarp();

@@ -294,13 +294,20 @@ void Engine::destroy()
     if (device >= 0) cudaSetDevice(device);
     DeviceBuffer* bufs[] = {&seq_q_, &seq_s_, &seq_qr_, &seq_sr_, &col_, &rowH_, &rowF_, &corner_,
                             &progress_, &jobs_, &misc_, &lut_, &col2_, &aux_, &aux2_, &pred_,
-                            &tb_out_, &blockmax_, &edges_, &multi_};
+                            &tb_out_, &blockmax_, &edges_, &multi_, &p2_[0], &p2_[1]};
     drop_host_batch_stream();
     for (DeviceBuffer* b : bufs) b->release();
     if (h_misc_) cudaFreeHost(h_misc_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    for (int i = 0; i < 2; ++i) {
+        if (p2_ready_[i]) cudaEventDestroy(p2_ready_[i]);
+        if (p2_done_[i]) cudaEventDestroy(p2_done_[i]);
+        p2_ready_[i] = p2_done_[i] = nullptr;
+    }
+    copy_stream_ = nullptr;
     h_misc_ = nullptr; ev0_ = ev1_ = nullptr; stream_ = nullptr;
 }
 

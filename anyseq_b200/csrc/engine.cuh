@@ -10,6 +10,8 @@
 
 namespace anyseq {
 
+struct BatchArgs;   // batch.cuh
+
 // grow-only device allocation
 struct DeviceBuffer {
     void* ptr = nullptr;
@@ -97,6 +99,11 @@ public:
     int score_batch_host(const anyseq_scoring& sc, const char* q, const int64_t* qoff,
                          const char* s, const int64_t* soff, int64_t npairs, int32_t* scores,
                          anyseq_result* out);
+    // 2-bit packed DNA batches (batch_packed2.cu)
+    int score_batch_packed2_device(const anyseq_scoring& sc, const anyseq_packed_batch& b, int32_t* d_scores,
+                                   anyseq_result* out);
+    int score_batch_packed2_host(const anyseq_scoring& sc, const anyseq_packed_batch& b, int32_t* scores,
+                                 anyseq_result* out);
     int measure_int_peak(int kind, double* ops_per_s, float* sm_mhz);
 
     int inbox_create(int rows, Inbox** out, void* handle64);
@@ -121,6 +128,8 @@ private:
     int pick_K(int n, bool chained = false) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int pick_band(int m, int nstrips, int resident, int K) const;
+    int launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool affine, BatchArgs& ba, int max_long,
+                     int max_short, cudaStream_t st);
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
@@ -133,6 +142,9 @@ private:
     DeviceBuffer multi_;         // score_strip_device_multi: per-pair border/row/corner/progress/result storage
     DeviceBuffer edges_;         // full-matrix traceback: right edge column (H, E) of every 128-column strip
     DeviceBuffer blockmax_;      // local end-cell tracking: one key per 1024 x 1024 reference block
+    DeviceBuffer p2_[2];         // packed2 host pipeline: two device chunk slots
+    cudaStream_t copy_stream_ = nullptr;                     // packed2 host pipeline: H2D of chunk c+1 under the kernel of chunk c
+    cudaEvent_t p2_ready_[2] = {nullptr, nullptr}, p2_done_[2] = {nullptr, nullptr};
     int* h_misc_ = nullptr;           // pinned mirror of misc_
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
     std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)

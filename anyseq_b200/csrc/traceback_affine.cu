@@ -21,6 +21,8 @@
 #include "strip_kernel.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace anyseq {
@@ -300,7 +302,9 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
     std::vector<Job> jobs;
     std::vector<HbPartA> parts;
 
+    const bool trace_levels = std::getenv("ANYSEQ_TRACE_LEVELS") != nullptr;   // development: per-level host time on stderr
     while (part_width > kMinPartWA) {
+        const auto lvl_t0 = std::chrono::steady_clock::now();
         const int half = part_width / 2;
         const int num_halfs = (n + half - 1) / part_width * 2;
         const int nparts = num_halfs / 2;
@@ -373,6 +377,10 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
         if (h_misc_[kMiscStatus] != kStatusOk) {
             set_last_error("strip kernel watchdog fired during a Hirschberg level");
             return ANYSEQ_ERR_KERNEL_TIMEOUT;
+        }
+        if (trace_levels) {
+            const double lvl_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lvl_t0).count();
+            std::fprintf(stderr, "[anyseq level] part_width=%d parts=%d jobs=%zu K=%d: %.2f ms\n", part_width, nparts, jobs.size(), K, lvl_ms);
         }
         part_width /= 2;
         bpp /= 2;

@@ -187,6 +187,33 @@ int anyseq_score_batch_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                               const void* d_subjects, const int64_t* d_s_off,
                               int64_t npairs, int32_t* d_scores, anyseq_result* out);
 
+/* 2-bit packed batches (DNA reads x windows, BASELINE configs[3]; the packed staging of the reference is
+ * sequence_to_device, src/mapping_acc.impala:125-131, one byte per symbol).  Four symbols per byte, least significant
+ * bits first, A/C/G/T (either case) = 0/1/2/3; every sequence starts on a byte boundary.  Symbols are compared by
+ * value, exactly like the byte path compares bytes (src/align.impala:132), so scores equal those of the unpacked
+ * sequences.  Sequence p of the queries starts at byte q_boff[p] (q_boff == NULL: at p * q_stride) and has q_len[p]
+ * symbols (q_len == NULL: q_len_uniform); same for the subjects.  A quarter of the bytes of the byte path cross
+ * PCIe, and no alphabet analysis pass is needed.  Host variant: chunks are copied straight from the caller's memory
+ * (pin it for full H2D speed) on a copy stream while the previous chunk is relaxed; scores land in `scores`. */
+typedef struct anyseq_packed_batch {
+    const uint8_t* q2;
+    const uint8_t* s2;
+    const int64_t* q_boff;
+    const int64_t* s_boff;
+    const int32_t* q_len;
+    const int32_t* s_len;
+    int32_t q_len_uniform, s_len_uniform;
+    int64_t q_stride, s_stride;
+    int64_t npairs;
+} anyseq_packed_batch;
+int anyseq_score_batch_packed2(anyseq_ctx* ctx, const anyseq_scoring* sc, const anyseq_packed_batch* host_batch,
+                               int32_t* scores, anyseq_result* out);
+int anyseq_score_batch_packed2_device(anyseq_ctx* ctx, const anyseq_scoring* sc, const anyseq_packed_batch* device_batch,
+                                      int32_t* d_scores, anyseq_result* out);
+/* Producer-side helper: packs n symbols (A/C/G/T, either case) into ceil(n/4) bytes of out; returns the number of
+ * symbols that are not A/C/G/T (they cannot be represented: use the byte path for such sequences). */
+int64_t anyseq_pack2(const char* seq, int64_t n, uint8_t* out);
+
 /* Streaming batches (many-record FASTA/FASTQ x windows ingestion that is not H2D-bound).
  * A stream owns `slots` chunk slots of PINNED host memory + device memory.  One producer thread
  *   acquire (blocks for a free slot) -> fill queries/q_off/subjects/s_off/npairs -> submit (starts H2D)

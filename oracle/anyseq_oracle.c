@@ -1025,3 +1025,30 @@ int64_t oracle_alignment_column_score_affine(const uint8_t* aq, const uint8_t* a
     }
     return t;
 }
+
+/* ========================================================================
+ * Batches of independent pairs (BASELINE configs[3]): every pair goes through
+ * oracle_score_affine / oracle_score_linear above with a team of ONE thread
+ * (a 150 x 500 pair is a single 1024 x 1024 block anyway); the pairs are
+ * spread over `threads` host threads.  scores[p] = score of pair p.
+ * ====================================================================== */
+void oracle_score_batch(int mode, const uint8_t* q, const int64_t* qoff, const uint8_t* s, const int64_t* soff,
+                        int64_t npairs, int same, int diff, int gi, int ge, int threads, int32_t* scores)
+{
+    if (threads < 1) threads = 1;
+    #pragma omp parallel for num_threads(threads) schedule(dynamic, 64)
+    for (int64_t p = 0; p < npairs; ++p) {
+        const int m = (int)(qoff[p + 1] - qoff[p]), n = (int)(soff[p + 1] - soff[p]);
+        oracle_result r;
+        if (m == 0 || n == 0) {
+            /* no block ever runs (quirk Q12): global leaves the init value, semiglobal 0, local SCORE_MIN */
+            const int L = m > n ? m : n;
+            r.score = mode == ORACLE_GLOBAL ? (L > 0 ? gi + L * ge : 0) : (mode == ORACLE_SEMIGLOBAL ? 0 : ORACLE_SCORE_MIN);
+        } else if (gi != 0) {
+            r = oracle_score_affine(mode, q + qoff[p], m, s + soff[p], n, same, diff, gi, ge, 1, 0, 0);
+        } else {
+            r = oracle_score_linear(mode, q + qoff[p], m, s + soff[p], n, same, diff, ge, 1, 0, 0);
+        }
+        scores[p] = r.score;
+    }
+}

@@ -135,6 +135,11 @@ void oracle_reference_random_pair(int64_t minlen, int64_t maxlen,
 
 uint64_t oracle_fnv1a64(const uint8_t* p, int64_t n);
 
+/* batch of independent pairs (packed back to back, offsets arrays of npairs + 1 entries): every pair through the
+ * restated path above with a team of one thread, pairs spread over `threads` host threads */
+void oracle_score_batch(int mode, const uint8_t* q, const int64_t* qoff, const uint8_t* s, const int64_t* soff,
+                        int64_t npairs, int same, int diff, int gap_init, int gap_extend, int threads, int32_t* scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ def lib():
     L.oracle_alignment_column_score.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.oracle_reference_random_pair.restype = None
     L.oracle_reference_random_pair.argtypes = [C.c_int64, C.c_int64, u8p, C.POINTER(C.c_int), u8p, C.POINTER(C.c_int)]
+    L.oracle_score_batch.restype = None
+    L.oracle_score_batch.argtypes = [C.c_int, u8p, C.POINTER(C.c_int64), u8p, C.POINTER(C.c_int64), C.c_int64,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.oracle_fnv1a64.restype = C.c_uint64
     L.oracle_fnv1a64.argtypes = [u8p, C.c_int64]
     _lib = L
@@ -138,6 +141,19 @@ def fullsize_score(mode, q, s, same=2, diff=-1, gap_init=-2, gap_extend=-1, thre
     q, s = _u8(q), _u8(s)
     r = lib().fullsize_score(_mode(mode), _ptr(q), len(q), _ptr(s), len(s), same, diff, gap_init, gap_extend, threads)
     return r.score, r.pos_i, r.pos_j
+
+
+def score_batch(mode, q, q_off, s, s_off, same=2, diff=-1, gap_init=-2, gap_extend=-1, threads=4) -> np.ndarray:
+    """scores of a batch of independent pairs (packed sequences + offsets), pair by pair through the restated path"""
+    q, s = _u8(q), _u8(s)
+    qo = np.ascontiguousarray(q_off, dtype=np.int64)
+    so = np.ascontiguousarray(s_off, dtype=np.int64)
+    n = len(qo) - 1
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    i64p = C.POINTER(C.c_int64)
+    lib().oracle_score_batch(_mode(mode), _ptr(q), qo.ctypes.data_as(i64p), _ptr(s), so.ctypes.data_as(i64p), n,
+                             same, diff, gap_init, gap_extend, threads, out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out[:n]
 
 
 def textbook_linear(mode, q, s, same=2, diff=-1, gap=-1) -> int:

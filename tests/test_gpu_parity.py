@@ -798,3 +798,77 @@ def test_batch_packed_16bit_kernels(aligner, oracle):
                     else:
                         want = oracle.score_linear(mode, qs[p], ss[p], sch.same, sch.diff, sch.gap_extend)[0]
                     assert got[p] == want, (lq, ls, mode, sch, p)
+
+
+def test_batch_packed2_vs_oracle_and_byte_path(aligner, oracle):
+    """anyseq_score_batch_packed2 (2-bit packed DNA, BASELINE configs[3] shape and ragged shapes): host pipeline and
+    device-resident entry, uniform strides and explicit offsets/lengths, all schemes -- scores must equal the byte
+    path (anyseq_score_batch) and the restated reference (oracle.score_batch)"""
+    import torch
+    import anyseq_b200 as A
+    from anyseq_b200 import capi, workloads as W
+    L = capi.load_library()
+    # (1) uniform reads x windows, chunked (batch_chunk_pairs small so that several chunks and both slots are used)
+    npairs = 5003
+    q, qo, s, so = W.read_batch(npairs, 150, 500, seed=11)
+    q2 = A.pack2(q.reshape(npairs, 150)); s2 = A.pack2(s.reshape(npairs, 500))
+    assert q2.shape == (npairs, 38) and s2.shape == (npairs, 125)
+    # the C helper packs like the numpy one
+    one = np.zeros(38, dtype=np.uint8)
+    assert L.anyseq_pack2(C.c_void_p(q[:150].ctypes.data), 150, C.c_void_p(one.ctypes.data)) == 0
+    assert bytes(one) == bytes(q2[0])
+    aligner.set_option("batch_chunk_pairs", 1024)
+    try:
+        for mode in MODES:
+            for sch in (A.affine_scoring_scheme(2, -1, -2, -1), A.linear_scoring_scheme(2, -1, -1)):
+                want = oracle.score_batch(mode, q, qo, s, so, sch.same, sch.diff, sch.gap_init, sch.gap_extend, threads=8)
+                pb = capi.PackedBatch(q2.ctypes.data, s2.ctypes.data, None, None, None, None, 150, 500, 38, 125, npairs)
+                got = np.full(npairs, -12345, dtype=np.int32)
+                aligner.score_batch_packed2(mode, pb, got.ctypes.data, sch)
+                assert np.array_equal(got, want), (mode, sch, np.flatnonzero(got != want)[:5])
+                byte_path, _ = aligner.score_batch(mode, q, qo, s, so, sch)
+                assert np.array_equal(byte_path, want)
+                # device-resident entry
+                dq = torch.from_numpy(q2).cuda(); ds = torch.from_numpy(s2).cuda()
+                dsc = torch.full((npairs,), -1, dtype=torch.int32, device="cuda")
+                pbd = capi.PackedBatch(dq.data_ptr(), ds.data_ptr(), None, None, None, None, 150, 500, 38, 125, npairs)
+                aligner.score_batch_packed2(mode, pbd, dsc.data_ptr(), sch, device=True)
+                assert np.array_equal(dsc.cpu().numpy(), want)
+    finally:
+        aligner.set_option("batch_chunk_pairs", 1 << 18)
+    # (2) ragged shapes with explicit byte offsets and lengths (incl. empty sequences and lengths not divisible by 4)
+    rng = np.random.default_rng(5)
+    n2 = 777
+    ql = rng.integers(0, 200, n2).astype(np.int32); sl = rng.integers(0, 700, n2).astype(np.int32)
+    ql[:3] = (0, 1, 5); sl[:3] = (9, 0, 3)
+    qs = [_rand(rng, int(x)) for x in ql]
+    ss = []
+    for a, x in zip(qs, sl):
+        w = _rand(rng, int(x))
+        if len(a) and x > len(a) + 5:
+            o = int(rng.integers(0, x - len(a)))
+            w[o:o + len(a)] = a
+            w[o + len(a) // 2] = ord("A")
+        ss.append(w)
+    qb = np.zeros(n2, dtype=np.int64); sb = np.zeros(n2, dtype=np.int64)
+    qparts, sparts = [], []
+    qpos = spos = 0
+    for i in range(n2):
+        qb[i] = qpos; sb[i] = spos
+        pq = A.pack2(qs[i]).reshape(-1) if len(qs[i]) else np.zeros(0, dtype=np.uint8)
+        ps = A.pack2(ss[i]).reshape(-1) if len(ss[i]) else np.zeros(0, dtype=np.uint8)
+        qparts.append(pq); sparts.append(ps)
+        qpos += len(pq) + (i % 3)            # gaps between sequences are allowed
+        spos += len(ps)
+        qparts.append(np.zeros(i % 3, dtype=np.uint8))
+    q2r = np.concatenate(qparts + [np.zeros(8, dtype=np.uint8)]); s2r = np.concatenate(sparts + [np.zeros(8, dtype=np.uint8)])
+    qcat = np.concatenate(qs); scat = np.concatenate(ss)
+    qoff = np.concatenate([[0], np.cumsum(ql)]).astype(np.int64); soff = np.concatenate([[0], np.cumsum(sl)]).astype(np.int64)
+    for mode in MODES:
+        sch = A.affine_scoring_scheme(2, -1, -3, -1)
+        want = oracle.score_batch(mode, qcat, qoff, scat, soff, sch.same, sch.diff, sch.gap_init, sch.gap_extend, threads=8)
+        pb = capi.PackedBatch(q2r.ctypes.data, s2r.ctypes.data, qb.ctypes.data, sb.ctypes.data, ql.ctypes.data, sl.ctypes.data,
+                              0, 0, 0, 0, n2)
+        got = np.full(n2, -12345, dtype=np.int32)
+        aligner.score_batch_packed2(mode, pb, got.ctypes.data, sch)
+        assert np.array_equal(got, want), (mode, np.flatnonzero(got != want)[:5])
