@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "global_alignment_score", "semiglobal_alignment_score", "local_alignment_score",
     "construct_global_alignment", "construct_semiglobal_alignment", "construct_local_alignment",
     "construct_global_alignment_fulltb", "construct_semiglobal_alignment_fulltb", "construct_local_alignment_fulltb",
-    "anyseq_align_full",
+    "anyseq_align_full", "anyseq_align_sharded",
     "anyseq_ctx_create", "anyseq_ctx_destroy", "anyseq_last_error", "anyseq_ctx_tune", "anyseq_ctx_set_option",
     "anyseq_score", "anyseq_score_device", "anyseq_align", "anyseq_last_splits", "anyseq_last_split_types", "anyseq_cigar",
     "anyseq_score_batch", "anyseq_score_batch_device",
@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "anyseq_batch_stream_open", "anyseq_batch_stream_acquire", "anyseq_batch_stream_submit", "anyseq_batch_stream_finish",
     "anyseq_batch_stream_collect", "anyseq_batch_stream_release", "anyseq_batch_stream_stats", "anyseq_batch_stream_close",
     "anyseq_strip_inbox_create", "anyseq_strip_inbox_open", "anyseq_strip_inbox_reset",
-    "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_score_strip_device_multi", "anyseq_strip_combine",
+    "anyseq_strip_inbox_destroy", "anyseq_score_strip_device", "anyseq_score_strip", "anyseq_score_strip_device_multi", "anyseq_strip_combine",
     "anyseq_measure_int_peak", "anyseq_device_info",
 ]
 
@@ -68,6 +68,10 @@ class BatchChunk(C.Structure):
                 ("cap_pairs", C.c_int64), ("cap_query_bytes", C.c_int64), ("cap_subject_bytes", C.c_int64),
                 ("npairs", C.c_int64), ("scores", C.POINTER(C.c_int32)),
                 ("kernel_ms", C.c_float), ("slot", C.c_int32)]
+
+
+# anyseq_bcast_fn: int (*)(void* user, void* d_buffer, int64_t nbytes, int src_rank)
+BCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int)
 
 
 class AnyseqError(RuntimeError):
@@ -160,12 +164,18 @@ def load_library(path: str | None = None):
     L.anyseq_score_strip_device.restype = C.c_int
     L.anyseq_score_strip_device.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                             vp, vp, C.POINTER(StripPartial)]
+    L.anyseq_score_strip.restype = C.c_int
+    L.anyseq_score_strip.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                     vp, vp, C.POINTER(StripPartial)]
     L.anyseq_score_strip_device_multi.restype = C.c_int
     L.anyseq_score_strip_device_multi.argtypes = [vp, C.POINTER(Scoring), C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
                                                   C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp),
                                                   C.POINTER(StripPartial)]
     L.anyseq_strip_combine.restype = C.c_int
     L.anyseq_strip_combine.argtypes = [C.POINTER(Scoring), C.POINTER(StripPartial), C.c_int, C.POINTER(Result)]
+    L.anyseq_align_sharded.restype = C.c_int
+    L.anyseq_align_sharded.argtypes = [vp, C.POINTER(Scoring), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, BCAST_FN, vp,
+                                       vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Result)]
     L.anyseq_measure_int_peak.restype = C.c_int
     L.anyseq_measure_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.anyseq_device_info.restype = C.c_int

@@ -230,6 +230,15 @@ int anyseq_score_strip_device(anyseq_ctx* ctx, const anyseq_scoring* sc, const v
                                        next_inbox ? &next_inbox->box : nullptr, out);
 }
 
+int anyseq_score_strip(anyseq_ctx* ctx, const anyseq_scoring* sc, const char* query, int lenq,
+                       const char* subject_slice, int col_begin, int col_end, int lens_total,
+                       anyseq_inbox* inbox, anyseq_inbox* next_inbox, anyseq_strip_partial* out)
+{
+    if (!ctx || !sc || !out) return ANYSEQ_ERR_BAD_ARG;
+    return ctx->eng.score_strip_host(*sc, query, lenq, subject_slice, col_begin, col_end, lens_total,
+                                     inbox ? &inbox->box : nullptr, next_inbox ? &next_inbox->box : nullptr, out);
+}
+
 int anyseq_score_strip_device_multi(anyseq_ctx* ctx, const anyseq_scoring* sc, int npairs, const void* const* d_query,
                                     int lenq, const void* const* d_subject_slice, int col_begin, int col_end,
                                     int lens_total, anyseq_inbox* const* inbox, anyseq_inbox* const* next_inbox,
@@ -296,6 +305,22 @@ int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* p
         out->score = best;
     }
     return ANYSEQ_OK;
+}
+
+int anyseq_align_sharded(anyseq_ctx* ctx, const anyseq_scoring* sc, const char* query, int lenq, const char* subject, int lens,
+                         int rank, int world, anyseq_bcast_fn bcast, void* user, char* alQuery, char* alSubject,
+                         int64_t* out_lo, int64_t* out_hi, anyseq_result* out)
+{
+    if (!ctx || !sc || !out || !alQuery || !alSubject || !out_lo || !out_hi) return ANYSEQ_ERR_BAD_ARG;
+    anyseq::TracebackShard sh;
+    sh.rank = rank;
+    sh.world = world;
+    sh.bcast = bcast;
+    sh.user = user;
+    const int rc = ctx->eng.align_host_sharded(*sc, query, lenq, subject, lens, alQuery, alSubject, out, &sh);
+    *out_lo = sh.out_lo;
+    *out_hi = sh.out_hi;
+    return rc;
 }
 
 int anyseq_measure_int_peak(anyseq_ctx* ctx, int kind, double* ops_per_s, float* sm_mhz_est)

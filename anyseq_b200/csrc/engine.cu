@@ -758,6 +758,20 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
     return ANYSEQ_OK;
 }
 
+int Engine::score_strip_host(const anyseq_scoring& sc, const char* q, int m, const char* s_slice, int col_begin, int col_end,
+                             int n_total, Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out)
+{
+    const int w = col_end - col_begin;
+    if (m < 1 || w < 1 || !q || !s_slice || !out) { set_last_error("bad arguments"); return ANYSEQ_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    ANYSEQ_CUDA_CHECK(cudaSetDevice(device));
+    if (seq_q_.ensure((size_t)m + 64) || seq_s_.ensure((size_t)w + 64)) return ANYSEQ_ERR_NO_DEVICE;
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_q_.ptr, q, (size_t)m, cudaMemcpyHostToDevice, stream_));
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_s_.ptr, s_slice, (size_t)w, cudaMemcpyHostToDevice, stream_));
+    return score_strip_device(sc, seq_q_.as<uint8_t>(), m, seq_s_.as<uint8_t>(), col_begin, col_end, n_total, inbox,
+                              next_inbox, out);
+}
+
 int Engine::score_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                        anyseq_result* out)
 {

@@ -69,6 +69,19 @@ struct Inbox {            // left-border mailbox of a rank (multi-GPU wavefront)
     static size_t bytes_for(int rows) { return sizeof(int4) * (size_t)rows + 256; }
 };
 
+// Multi-GPU linear-space traceback (one process per GPU): the halves of a Hirschberg level are
+// independent DP problems (iteration_partitioned, src/iteration_cpu.impala:59-119), so they are dealt out to the ranks:
+// half h of a level with P parts belongs to rank h / (2P / world) once 2P >= world (a rank then owns whole parts and
+// needs nothing from anybody), and to rank h * (world / 2P) on the first log2(world) levels, where the two halves of a
+// part sit on different ranks and their last-column records are broadcast before hb_sum
+// (src/traceback_lintime.impala:44-135) runs on every rank.  Every rank finally emits the 128-column blocks of its parts.
+struct TracebackShard {
+    int rank = 0, world = 1;
+    anyseq_bcast_fn bcast = nullptr;   // broadcast of a device buffer from src_rank to all ranks (caller: NCCL)
+    void* user = nullptr;
+    long long out_lo = 0, out_hi = 0;  // [out] index range of the output strings this rank produced
+};
+
 class Engine {
 public:
     int init(int device);
@@ -81,6 +94,8 @@ public:
     int score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int m,
                            const uint8_t* d_s_slice, int col_begin, int col_end, int n_total,
                            Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out);
+    int score_strip_host(const anyseq_scoring& sc, const char* q, int m, const char* s_slice, int col_begin, int col_end,
+                         int n_total, Inbox* inbox, Inbox* next_inbox, anyseq_strip_partial* out);
     // several pairs of the SAME shape (lenq, slice) in one launch, their items interleaved band by band: a narrow
     // multi-GPU slice has too few strips to fill the SMs, two of them side by side do (engine.cu)
     int score_strip_device_multi(const anyseq_scoring& sc, int npairs, const uint8_t* const* d_q, int m,
@@ -90,6 +105,10 @@ public:
                    char* alq, char* als, anyseq_result* out);
     int align_host_affine(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                           char* alq, char* als, anyseq_result* out);
+    // this rank's share of a traceback spread over `shard.world` GPUs (traceback.cu); alq/als are full-size buffers of
+    // which only [shard.out_lo, shard.out_hi) is meaningful afterwards
+    int align_host_sharded(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
+                           char* alq, char* als, anyseq_result* out, TracebackShard* shard);
     // full-matrix traceback (traceback_full.cu); start2 = get_alignment_start()
     int align_full_host(const anyseq_scoring& sc, const char* q, int m, const char* s, int n,
                         char* alq, char* als, anyseq_result* out, int* start2);
@@ -156,6 +175,7 @@ private:
     int last_start_[2] = {0, 0}; // get_alignment_start() of the last full-matrix traceback
     bool track_ = false;         // the running score call tracks the local end cell
     int init_col0_ = 0;               // absolute column of the job's first column (multi-GPU)
+    TracebackShard* shard_ = nullptr; // set while align_host_sharded runs
     std::recursive_mutex mu_;
 };
 

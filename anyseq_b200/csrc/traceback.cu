@@ -111,6 +111,7 @@ __global__ void trace_dp_kernel(const uint8_t* __restrict__ q, const uint8_t* __
     const int wpb = blockDim.x >> 5;
     for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
         const int off = blk_off[b], h = blk_h[b];
+        if (h < 0) continue;                                        // block of another rank (sharded traceback)
         const int oj = b * kMinPartW;
         int H[4], sc[4];
 #pragma unroll
@@ -164,6 +165,7 @@ __global__ void trace_walk_kernel(const uint8_t* __restrict__ q, const uint8_t* 
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const int off = blk_off[b], h = blk_h[b];
+    if (h < 0) return;                                              // block of another rank (sharded traceback)
     const int oj = b * kMinPartW;
     const int w = min(kMinPartW, n - oj);
     auto P = [&](int i, int j) -> int {
@@ -184,6 +186,13 @@ __global__ void trace_walk_kernel(const uint8_t* __restrict__ q, const uint8_t* 
         out_s[ob + pos] = ss;
         p = P(i, j);
     }
+}
+
+// which rank relaxes half `h` (= 2 * part + side) of a level with `np_full` parts (see TracebackShard)
+int traceback_half_owner(int h, int np_full, int world)
+{
+    const int halves = 2 * np_full;
+    return halves >= world ? h / (halves / world) : h * (world / halves);
 }
 
 static int next_pow_2(int i)   // src/utils.impala:19-28
@@ -232,7 +241,8 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
 
     // true optimal score of the scheme (the reference returns the value of a
     // never-relaxed object here, quirk Q1; the legacy symbols reproduce that)
-    if (tune.align_with_score) {
+    const int srank = shard_ ? shard_->rank : 0, sworld = shard_ ? shard_->world : 1;
+    if (tune.align_with_score && !shard_) {
         anyseq_result tmp;
         rc = score_host(sc, q, m, s, n, &tmp);
         if (rc) return rc;
@@ -262,7 +272,8 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
     int part_width = next_pow_2(n);
     const int nb = (n + kMinPartW - 1) / kMinPartW;
     int bpp = part_width / kMinPartW;
-    std::vector<int> splits((size_t)nb + 1, 0);
+    const int full_width = part_width;
+    std::vector<int> splits((size_t)nb + 1, shard_ ? -1 : 0);       // sharded: -1 = decided by another rank
     splits[0] = 0;
     splits[nb] = m;
     auto part_dims = [&](int part, int* off, int* h) {
@@ -296,10 +307,16 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         const int SW = kWarp * K;
         const int resident = resident_warps(K, local, false, (n + SW - 1) / SW);
 
+        // sharded traceback: who relaxes which half of this level (TracebackShard)
+        const int np_full = full_width / part_width;
+        const bool shared_level = sworld > 1 && np_full < sworld;       // the halves of a part sit on different ranks
         jobs.clear();
         parts.clear();
         long long strip_total = 0;
         for (int p = 0; p < nparts; ++p) {
+            const int own_l = sworld > 1 ? traceback_half_owner(2 * p, np_full, sworld) : 0;
+            const int own_r = sworld > 1 ? traceback_half_owner(2 * p + 1, np_full, sworld) : 0;
+            if (!shared_level && own_l != srank) continue;              // a whole part of another rank
             int off, len;
             part_dims(p, &off, &len);
             const int c_left = 2 * p * half;
@@ -311,6 +328,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
             parts.push_back(hp);
             if (len <= 0) continue;
             for (int side = 0; side < 2; ++side) {
+                if ((side == 0 ? own_l : own_r) != srank) continue;
                 Job J;
                 std::memset(&J, 0, sizeof(J));
                 const int w = side == 0 ? half : rhw;
@@ -344,10 +362,26 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
             rc = run_jobs(jobs, sp, local, false, K, &launches);
             if (rc) return rc;
         }
-        if (aux2_.ensure(sizeof(HbPart) * (size_t)std::max(nparts, 1))) return ANYSEQ_ERR_NO_DEVICE;
-        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(aux2_.ptr, parts.data(), sizeof(HbPart) * (size_t)nparts, cudaMemcpyHostToDevice, stream_));
+        if (shared_level) {
+            // every rank needs the last-column records of BOTH halves of every part of this level: broadcast them from
+            // the ranks that relaxed them (16 bytes per query row and half; NVLink)
+            ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            for (int p = 0; p < (int)parts.size(); ++p) {
+                const HbPart& hp = parts[(size_t)p];
+                if (hp.len <= 0) continue;
+                rc = shard_->bcast(shard_->user, col_.as<int4>() + hp.off, (int64_t)sizeof(int4) * hp.len,
+                                   traceback_half_owner(2 * p, np_full, sworld));
+                if (!rc) rc = shard_->bcast(shard_->user, col2_.as<int4>() + hp.off, (int64_t)sizeof(int4) * hp.len,
+                                            traceback_half_owner(2 * p + 1, np_full, sworld));
+                if (rc) { set_last_error("sharded traceback: the broadcast callback failed"); return ANYSEQ_ERR_BAD_ARG; }
+            }
+        }
+        const int nparts_here = (int)parts.size();      // all parts of a shared level, else the parts of this rank
+        if (aux2_.ensure(sizeof(HbPart) * (size_t)std::max(nparts_here, 1))) return ANYSEQ_ERR_NO_DEVICE;
+        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(aux2_.ptr, parts.data(), sizeof(HbPart) * (size_t)nparts_here, cudaMemcpyHostToDevice, stream_));
         const int bpp2 = part_width / std::min(kRefBlockW, part_width);
-        hb_sum_kernel<<<std::min(nparts, 4096), 256, 0, stream_>>>(aux2_.as<HbPart>(), nparts, col_.as<int4>(),
+        if (nparts_here > 0)
+        hb_sum_kernel<<<std::min(nparts_here, 4096), 256, 0, stream_>>>(aux2_.as<HbPart>(), nparts_here, col_.as<int4>(),
                                                                    col2_.as<int4>(), d_splits, half, bpp2,
                                                                    init_global, sp.gap_extend);
         ANYSEQ_CUDA_CHECK(cudaGetLastError());
@@ -369,11 +403,24 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
 
     // final pass: blockwise relaxation with predecessors + walks
     std::vector<int> blk(2 * (size_t)nb);
+    const int blocks_full = std::max(1, full_width / kMinPartW);
+    long long out_lo = (long long)outlen, out_hi = 0;
     for (int b = 0; b < nb; ++b) {
+        const int owner = (sworld > 1 && blocks_full >= sworld) ? b / (blocks_full / sworld) : 0;
+        if (owner != srank) { blk[b] = 0; blk[nb + b] = -1; continue; }      // another rank's block: skipped by the kernels
         int off, h;
         part_dims(b, &off, &h);        // bpp == 1 here, or 0 for n <= 64 (quirk Q4: height 0)
         blk[b] = off;
         blk[nb + b] = h;
+        // the block writes output columns [off + 128 b, off + h + 128 b + w) only
+        out_lo = std::min(out_lo, (long long)off + (long long)b * kMinPartW);
+        out_hi = std::max(out_hi, (long long)off + h + (long long)b * kMinPartW + std::min(kMinPartW, n - b * kMinPartW));
+    }
+    if (shard_) {
+        // the ranges of the ranks tile [0, m + n): the first rank starts at 0, the last one ends at m + n
+        if (out_lo > out_hi) out_lo = out_hi = 0;
+        shard_->out_lo = out_lo;
+        shard_->out_hi = out_hi;
     }
     if (aux2_.ensure(sizeof(int) * 2 * (size_t)nb) || pred_.ensure((size_t)m * 32 + 64) ||
         tb_out_.ensure(2 * outlen + 64))
@@ -403,6 +450,22 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
     out->kernel_launches = launches;
     last_splits_ = splits;
     return ANYSEQ_OK;
+}
+
+int Engine::align_host_sharded(const anyseq_scoring& sc, const char* q, int m, const char* s, int n, char* alq, char* als,
+                               anyseq_result* out, TracebackShard* shard)
+{
+    if (!shard || shard->world < 1 || (shard->world & (shard->world - 1)) != 0 || shard->rank < 0 || shard->rank >= shard->world ||
+        (shard->world > 1 && !shard->bcast)) {
+        set_last_error("sharded traceback: world must be a power of two, 0 <= rank < world, and a broadcast callback is needed");
+        return ANYSEQ_ERR_BAD_ARG;
+    }
+    if (m < 1 || n < 1) { set_last_error("sharded traceback: empty sequence"); return ANYSEQ_ERR_BAD_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    struct Scope { TracebackShard*& p; ~Scope() { p = nullptr; } } scope{shard_};
+    shard_ = shard;
+    shard->out_lo = shard->out_hi = 0;
+    return align_host(sc, q, m, s, n, alq, als, out);
 }
 
 }  // namespace anyseq

@@ -27,6 +27,8 @@
 
 namespace anyseq {
 
+int traceback_half_owner(int h, int np_full, int world);   // traceback.cu
+
 constexpr int kMinPartWA = 128;     // MIN_PART_WIDTH_HB, src/align.impala:18
 constexpr int kRefBlockWA = 1024;   // BLOCK_WIDTH of the reference CPU build
 
@@ -122,6 +124,7 @@ __global__ void trace_dp_affine_kernel(const uint8_t* __restrict__ q, const uint
     const int go = gi + ge;
     for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
         const int off = blk_off[b], h = blk_h[b];
+        if (h < 0) continue;                                          // block of another rank (sharded traceback)
         const int open_top = blk_open_top[b];
         const int oj = b * kMinPartWA;
         const int w = min(kMinPartWA, n - oj);
@@ -188,6 +191,7 @@ __global__ void trace_walk_affine_kernel(const uint8_t* __restrict__ q, const ui
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const int off = blk_off[b], h = blk_h[b];
+    if (h < 0) return;                                                // block of another rank (sharded traceback)
     const int oj = b * kMinPartWA;
     const int w = min(kMinPartWA, n - oj);
     int i = h - 1, j = w - 1;
@@ -245,7 +249,8 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
     int launches = 0;
     float total_ms = 0.f;
 
-    if (tune.align_with_score) {
+    const int srank = shard_ ? shard_->rank : 0, sworld = shard_ ? shard_->world : 1;
+    if (tune.align_with_score && !shard_) {
         anyseq_result tmp;
         rc = score_host(sc, q, m, s, n, &tmp);
         if (rc) return rc;
@@ -273,7 +278,8 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
     int part_width = next_pow_2a(n);
     const int nb = (n + kMinPartWA - 1) / kMinPartWA;
     int bpp = part_width / kMinPartWA;
-    std::vector<int> splits((size_t)nb + 1, 0), types((size_t)nb + 1, 0);
+    const int full_width = part_width;
+    std::vector<int> splits((size_t)nb + 1, shard_ ? -1 : 0), types((size_t)nb + 1, 0);   // sharded: -1 = another rank's split
     splits[0] = 0;
     splits[nb] = m;
     auto part_dims = [&](int part, int* off, int* h, int* start_slot, int* end_slot) {
@@ -312,10 +318,16 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
         const int SW = kWarp * K;
         const int resident = resident_warps(K, local, true, (n + SW - 1) / SW);
 
+        // sharded traceback: who relaxes which half of this level (TracebackShard, traceback.cu)
+        const int np_full = full_width / part_width;
+        const bool shared_level = sworld > 1 && np_full < sworld;
         jobs.clear();
         parts.clear();
         long long strip_total = 0;
         for (int p = 0; p < nparts; ++p) {
+            const int own_l = sworld > 1 ? traceback_half_owner(2 * p, np_full, sworld) : 0;
+            const int own_r = sworld > 1 ? traceback_half_owner(2 * p + 1, np_full, sworld) : 0;
+            if (!shared_level && own_l != srank) continue;              // a whole part of another rank
             int off, len, s0, s1;
             part_dims(p, &off, &len, &s0, &s1);
             const int c_left = 2 * p * half;
@@ -329,6 +341,7 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
             parts.push_back(hp);
             if (len <= 0) continue;
             for (int side = 0; side < 2; ++side) {
+                if ((side == 0 ? own_l : own_r) != srank) continue;
                 Job J;
                 std::memset(&J, 0, sizeof(J));
                 const int w = side == 0 ? half : rhw;
@@ -362,10 +375,25 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
             rc = run_jobs(jobs, sp, local, true, K, &launches);
             if (rc) return rc;
         }
-        if (aux2_.ensure(sizeof(HbPartA) * (size_t)std::max(nparts, 1))) return ANYSEQ_ERR_NO_DEVICE;
-        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(aux2_.ptr, parts.data(), sizeof(HbPartA) * (size_t)nparts, cudaMemcpyHostToDevice, stream_));
+        if (shared_level) {
+            // both halves' last-column records (H and E: the E-type joins need both) to every rank
+            ANYSEQ_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            for (int p = 0; p < (int)parts.size(); ++p) {
+                const HbPartA& hp = parts[(size_t)p];
+                if (hp.len <= 0) continue;
+                rc = shard_->bcast(shard_->user, col_.as<int4>() + hp.off, (int64_t)sizeof(int4) * hp.len,
+                                   traceback_half_owner(2 * p, np_full, sworld));
+                if (!rc) rc = shard_->bcast(shard_->user, col2_.as<int4>() + hp.off, (int64_t)sizeof(int4) * hp.len,
+                                            traceback_half_owner(2 * p + 1, np_full, sworld));
+                if (rc) { set_last_error("sharded traceback: the broadcast callback failed"); return ANYSEQ_ERR_BAD_ARG; }
+            }
+        }
+        const int nparts_here = (int)parts.size();
+        if (aux2_.ensure(sizeof(HbPartA) * (size_t)std::max(nparts_here, 1))) return ANYSEQ_ERR_NO_DEVICE;
+        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(aux2_.ptr, parts.data(), sizeof(HbPartA) * (size_t)nparts_here, cudaMemcpyHostToDevice, stream_));
         const int bpp2 = part_width / std::min(kRefBlockWA, part_width);
-        hb_sum_affine_kernel<<<std::min(nparts, 4096), 256, 0, stream_>>>(aux2_.as<HbPartA>(), nparts, col_.as<int4>(),
+        if (nparts_here > 0)
+        hb_sum_affine_kernel<<<std::min(nparts_here, 4096), 256, 0, stream_>>>(aux2_.as<HbPartA>(), nparts_here, col_.as<int4>(),
                                                                           col2_.as<int4>(), d_splits, d_types, half, bpp2,
                                                                           glob, gi, ge);
         ANYSEQ_CUDA_CHECK(cudaGetLastError());
@@ -388,14 +416,25 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
 
     // final pass
     std::vector<int> blk(5 * (size_t)nb);
+    const int blocks_full = std::max(1, full_width / kMinPartWA);
+    long long out_lo = (long long)outlen, out_hi = 0;
     for (int b = 0; b < nb; ++b) {
+        const int owner = (sworld > 1 && blocks_full >= sworld) ? b / (blocks_full / sworld) : 0;
+        if (owner != srank) { blk[b] = 0; blk[nb + b] = -1; blk[2 * nb + b] = 0; blk[3 * nb + b] = 0; blk[4 * nb + b] = 0; continue; }
         int off, h, s0, s1;
         part_dims(b, &off, &h, &s0, &s1);
+        out_lo = std::min(out_lo, (long long)off + (long long)b * kMinPartWA);
+        out_hi = std::max(out_hi, (long long)off + h + (long long)b * kMinPartWA + std::min(kMinPartWA, n - b * kMinPartWA));
         blk[b] = off;
         blk[nb + b] = h;
         blk[2 * nb + b] = types[s0 + 1] ? 0 : gi;      // opening cost on the block's top border
         blk[3 * nb + b] = types[s1 + 1];               // end vertex type
         blk[4 * nb + b] = 0;
+    }
+    if (shard_) {
+        if (out_lo > out_hi) out_lo = out_hi = 0;
+        shard_->out_lo = out_lo;
+        shard_->out_hi = out_hi;
     }
     if (aux2_.ensure(sizeof(int) * 7 * (size_t)nb) || pred_.ensure((size_t)m * 64 + 128) || tb_out_.ensure(2 * outlen + 64))
         return ANYSEQ_ERR_NO_DEVICE;

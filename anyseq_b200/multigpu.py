@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
+
 from . import capi
 from .api import Aligner, AlignmentResult, ScoringScheme
 from .capi import Result, StripPartial, make_scoring
@@ -167,6 +169,24 @@ class StripWavefront:
         self.k = k + 1
         return part
 
+    def run_host(self, mode, scoring: ScoringScheme, query: np.ndarray, subject_slice: np.ndarray,
+                 col_begin: int, col_end: int, n_total: int) -> StripPartial:
+        """run() with HOST buffers (this rank's query and subject slice): anyseq_score_strip copies them to the device"""
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        part = StripPartial()
+        k = self.k
+        slot = (k % self.depth) * self.ppl
+        inbox, nxt = self.inboxes[slot], self.next_inboxes[slot]
+        if self.tokens is not None:
+            self.tokens.acquire(k)
+        self.al._check(self._lib.anyseq_score_strip(
+            self.al.handle, C.byref(sc), C.c_void_p(query.ctypes.data), len(query), C.c_void_p(subject_slice.ctypes.data),
+            col_begin, col_end, n_total, inbox if inbox else None, nxt if nxt else None, C.byref(part)))
+        if self.tokens is not None:
+            self.tokens.release(k)
+        self.k = k + 1
+        return part
+
     def run_multi(self, mode, scoring: ScoringScheme, d_queries, m: int, d_subject_slices,
                   col_begin: int, col_end: int, n_total: int):
         """len(d_queries) <= pairs_per_launch alignments of one shape in ONE launch -> list of StripPartial"""
@@ -214,3 +234,92 @@ class StripWavefront:
                 if h:
                     self._lib.anyseq_strip_inbox_destroy(self.al.handle, h)
                     lst[i] = C.c_void_p()
+
+
+# --------------------------------------------------------------------------- multi-GPU linear-space traceback
+def traceback_half_owner(h: int, np_full: int, world: int) -> int:
+    """rank that relaxes half h (= 2 * part + side) of a Hirschberg level with np_full parts -- the rule of
+    TracebackShard (csrc/engine.cuh): whole parts per rank once 2 * np_full >= world, before that one half per rank"""
+    halves = 2 * np_full
+    return h // (halves // world) if halves >= world else h * (world // halves)
+
+
+def merge_regions(lenq: int, lens: int, pieces):
+    """pieces: per rank (lo, hi, aligned_query[lo:hi], aligned_subject[lo:hi]) in rank order -> the two full strings.
+    The ranges of the ranks tile [0, lenq + lens) (a rank without blocks contributes an empty range)."""
+    total = lenq + lens
+    aq, as_ = bytearray(b" " * total), bytearray(b" " * total)
+    pos = 0
+    for lo, hi, q, s in pieces:
+        if hi <= lo:
+            continue
+        if lo != pos or len(q) != hi - lo or len(s) != hi - lo:
+            raise ValueError(f"traceback regions do not tile the output: expected a piece starting at {pos}, got [{lo}, {hi})")
+        aq[lo:hi] = q
+        as_[lo:hi] = s
+        pos = hi
+    if pos != total:
+        raise ValueError(f"traceback regions end at {pos}, not at {total}")
+    return bytes(aq), bytes(as_)
+
+
+def merge_splits(per_rank):
+    """split rows of all ranks (anyseq_last_splits, -1 = decided elsewhere) -> the single-GPU splits vector"""
+    out = np.max(np.asarray(per_rank, dtype=np.int64), axis=0)
+    return [int(x) for x in out]
+
+
+class _DevView:
+    """zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedTraceback:
+    """anyseq_align_sharded over torch.distributed: one process per GPU, world a power of two.  The library calls back
+    for every exchange of the first log2(world) Hirschberg levels (a broadcast of last-column border records, 16 bytes
+    per query row and half); it runs on NCCL over the raw device buffer.  gather() assembles the strings on every rank."""
+
+    def __init__(self, aligner: Aligner, rank: int, world: int, dist=None):
+        import torch
+        self.al, self.rank, self.world, self.dist, self._torch = aligner, rank, world, dist, torch
+        self._lib = capi.load_library()
+        self.bcast_bytes = 0
+
+        def _bcast(user, d_buffer, nbytes, src):
+            try:
+                t = torch.as_tensor(_DevView(d_buffer, nbytes), device="cuda")
+                self.dist.broadcast(t, src=int(src))
+                torch.cuda.synchronize()
+                self.bcast_bytes += int(nbytes)
+                return 0
+            except Exception as e:      # never let an exception cross the C boundary
+                print("ShardedTraceback: broadcast failed:", e, flush=True)
+                return 1
+
+        self._cb = capi.BCAST_FN(_bcast)
+
+    def align(self, mode, query, subject, scoring: ScoringScheme):
+        """-> (lo, hi, aligned_query[lo:hi], aligned_subject[lo:hi], splits of this rank, kernel_ms)"""
+        q, s = capi.as_u8(query), capi.as_u8(subject)
+        m, n = len(q), len(s)
+        sc = make_scoring(mode, scoring.same, scoring.diff, scoring.gap_init, scoring.gap_extend)
+        aq = np.empty(m + n, dtype=np.uint8)
+        as_ = np.empty(m + n, dtype=np.uint8)
+        lo, hi = C.c_int64(), C.c_int64()
+        res = Result()
+        self.al._check(self._lib.anyseq_align_sharded(
+            self.al.handle, C.byref(sc), capi._ptr(q), m, capi._ptr(s), n, self.rank, self.world, self._cb, None,
+            capi._ptr(aq), capi._ptr(as_), C.byref(lo), C.byref(hi), C.byref(res)))
+        return lo.value, hi.value, aq[lo.value:hi.value].tobytes(), as_[lo.value:hi.value].tobytes(), self.al.last_splits(), res.kernel_ms
+
+    def gather(self, m: int, n: int, piece):
+        """all-gather of the pieces -> (aligned_query, aligned_subject, splits) identical on every rank"""
+        lo, hi, q, s, splits, _ = piece
+        pieces = [(lo, hi, q, s, splits)]
+        if self.world > 1:
+            pieces = [None] * self.world
+            self.dist.all_gather_object(pieces, (lo, hi, q, s, splits))
+        aq, as_ = merge_regions(m, n, [(p[0], p[1], p[2], p[3]) for p in pieces])
+        return aq, as_, merge_splits([p[4] for p in pieces])

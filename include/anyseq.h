@@ -276,6 +276,12 @@ int anyseq_score_strip_device(anyseq_ctx* ctx, const anyseq_scoring* sc,
                               anyseq_inbox* inbox /* NULL on rank 0 */,
                               anyseq_inbox* next_inbox /* NULL on the last rank */,
                               anyseq_strip_partial* out);
+/* The same with HOST buffers (the rank's query and its slice of the subject): the call copies them to the device,
+ * like anyseq_score does on one GPU (sequence_to_device, src/mapping_acc.impala:125-131). */
+int anyseq_score_strip(anyseq_ctx* ctx, const anyseq_scoring* sc,
+                       const char* query, int lenq,
+                       const char* subject_slice, int col_begin, int col_end, int lens_total,
+                       anyseq_inbox* inbox, anyseq_inbox* next_inbox, anyseq_strip_partial* out);
 /* The same for `npairs` (<= 8) pairs of ONE shape (lenq, column range) in a single persistent launch, their work
  * items interleaved band by band.  A narrow slice alone has too few strips to occupy a B200; the slices of two
  * consecutive alignments of a stream side by side do.  Arrays of npairs device pointers / inboxes (inbox arrays may be
@@ -287,6 +293,21 @@ int anyseq_score_strip_device_multi(anyseq_ctx* ctx, const anyseq_scoring* sc, i
                                     anyseq_strip_partial* out);
 int anyseq_strip_combine(const anyseq_scoring* sc, const anyseq_strip_partial* parts, int nranks,
                          anyseq_result* out);
+
+/* Multi-GPU linear-space traceback (the halves of a Hirschberg level are independent, src/align.impala:254-259,
+ * src/iteration_cpu.impala:59-119).  Every rank (one process per GPU, world a power of two) calls it with the SAME
+ * sequences; the halves of every level are dealt out to the ranks, on the first log2(world) levels the last-column
+ * records of the halves are exchanged through `bcast` (the caller's collective, e.g. ncclBroadcast on the given device
+ * buffer; it must be complete when it returns), afterwards the ranks work independently.  alQuery / alSubject are
+ * lenq+lens-byte buffers of which this rank fills [*out_lo, *out_hi) -- the columns of its 128-column blocks; the
+ * ranges of all ranks tile [0, lenq+lens) in rank order, so concatenating them gives exactly the single-GPU strings.
+ * anyseq_last_splits afterwards holds -1 in the slots other ranks decided.  The optimal score is not computed here
+ * (use the strip wavefront, anyseq_score_strip*): out->score = 0. */
+typedef int (*anyseq_bcast_fn)(void* user, void* d_buffer, int64_t nbytes, int src_rank);
+int anyseq_align_sharded(anyseq_ctx* ctx, const anyseq_scoring* sc,
+                         const char* query, int lenq, const char* subject, int lens,
+                         int rank, int world, anyseq_bcast_fn bcast, void* user,
+                         char* alQuery, char* alSubject, int64_t* out_lo, int64_t* out_hi, anyseq_result* out);
 
 /* Measured integer-pipe peak of this GPU for the DP instruction mix (the
  * roofline denominator): runs dependency-free loops of the named

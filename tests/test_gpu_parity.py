@@ -872,3 +872,76 @@ def test_batch_packed2_vs_oracle_and_byte_path(aligner, oracle):
         got = np.full(n2, -12345, dtype=np.int32)
         aligner.score_batch_packed2(mode, pb, got.ctypes.data, sch)
         assert np.array_equal(got, want), (mode, np.flatnonzero(got != want)[:5])
+
+
+def test_sharded_traceback_equals_single_gpu(oracle):
+    """anyseq_align_sharded (multi-GPU linear-space traceback) with 2 and 4 ranks emulated by threads on
+    ONE GPU (one engine per rank, the broadcast callback copies between their buffers): the concatenated pieces and the
+    merged split rows must be bit-identical to the single-GPU traceback and to the restated reference, for linear and
+    Gotoh gaps, all three schemes"""
+    import threading
+    import torch
+    import anyseq_b200 as A
+    from anyseq_b200 import capi
+    from anyseq_b200.multigpu import ShardedTraceback, _DevView, merge_regions, merge_splits
+    rng = np.random.default_rng(21)
+    q = _rand(rng, 3111)
+    s = _related(rng, q, 5003, sub=0.07)
+    for world in (2, 4):
+        als = [A.Aligner(0) for _ in range(world)]
+        try:
+            for sch in (A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1)):
+                for mode in MODES:
+                    bar = threading.Barrier(world)
+                    slot = {}
+                    pieces = [None] * world
+                    errors = []
+
+                    def make_cb(rank):
+                        def cb(user, ptr, nbytes, src):
+                            try:
+                                if rank == src:
+                                    slot["ptr"] = ptr
+                                bar.wait(timeout=60)
+                                if rank != src:
+                                    dst = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+                                    dst.copy_(torch.as_tensor(_DevView(slot["ptr"], nbytes), device="cuda"))
+                                    torch.cuda.synchronize()
+                                bar.wait(timeout=60)
+                                return 0
+                            except Exception as e:          # pragma: no cover
+                                errors.append(e)
+                                return 1
+                        return capi.BCAST_FN(cb)
+
+                    def worker(rank):
+                        try:
+                            st = ShardedTraceback(als[rank], rank, world, dist=None)
+                            st._cb = make_cb(rank)
+                            pieces[rank] = st.align(mode, q, s, sch)
+                        except Exception as e:
+                            errors.append(e)
+                            bar.abort()
+
+                    ths = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+                    for t in ths:
+                        t.start()
+                    for t in ths:
+                        t.join()
+                    assert not errors, errors
+                    aq, as_ = merge_regions(len(q), len(s), [(p[0], p[1], p[2], p[3]) for p in pieces])
+                    splits = merge_splits([p[4] for p in pieces])
+                    als[0].set_option("align_with_score", 0)
+                    one = als[0].align(mode, q, s, sch)
+                    assert (aq, as_) == (one.aligned_query, one.aligned_subject), (world, mode, sch)
+                    assert splits == als[0].last_splits(), (world, mode, sch)
+                    if sch.affine:
+                        ref = oracle.traceback_lintime_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                    else:
+                        ref = oracle.traceback_lintime(mode, q, s, sch.same, sch.diff, sch.gap_extend)
+                    assert (aq, as_) == (ref[1], ref[2]), (world, mode, sch)
+                    # every rank did real work: no piece is empty and the regions tile the output
+                    assert all(p[1] > p[0] for p in pieces)
+        finally:
+            for a in als:
+                a.close()

@@ -223,3 +223,60 @@ def test_reader_and_printer_match_the_reference_host_code():
         assert mine == gold["print_alignment"] and mine["stdout"].count("<<<") == len(G.ALN_CASES)
         if os.path.exists(os.path.join(G.REF, "alignment_io.cpp")):
             assert G.run_printer(G.build_ref_printer(td)) == mine
+
+
+_TB_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+from anyseq_b200.multigpu import merge_regions, merge_splits, traceback_half_owner
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+m, n = 700, 900
+full = (b"Q" * 350 + b"_" * 450 + b"q" * 800, b"S" * 1600)
+# rank r owns the output columns of its blocks: here simply two unequal contiguous ranges
+lo, hi = (0, 650) if rank == 0 else (650, m + n)
+splits = [0, 100, -1, -1, 700] if rank == 0 else [0, -1, 300, 420, 700]      # -1 = decided by the other rank
+pieces = [None] * world
+dist.all_gather_object(pieces, (lo, hi, full[0][lo:hi], full[1][lo:hi], splits))
+aq, as_ = merge_regions(m, n, [(p[0], p[1], p[2], p[3]) for p in pieces])
+assert (aq, as_) == full
+assert merge_splits([p[4] for p in pieces]) == [0, 100, 300, 420, 700]
+# a gap between the regions is an error, not silently blanked
+try:
+    merge_regions(m, n, [(0, 600, full[0][:600], full[1][:600]), (650, m + n, full[0][650:], full[1][650:])])
+    raise SystemExit("gap not detected")
+except ValueError:
+    pass
+# ownership rule of the halves (csrc/traceback.cu: traceback_half_owner): level 0 of 2 ranks = one half each, later
+# levels whole parts; every half has exactly one owner and the owners are monotone in h
+for w in (1, 2, 4, 8):
+    for np_full in (1, 2, 4, 8, 16, 64):
+        owners = [traceback_half_owner(h, np_full, w) for h in range(2 * np_full)]
+        assert owners == sorted(owners) and 0 <= owners[0] and owners[-1] < w
+        if 2 * np_full >= w:
+            assert sorted(set(owners)) == list(range(w))
+            if np_full >= w:
+                assert all(owners[2 * p] == owners[2 * p + 1] for p in range(np_full))
+assert [traceback_half_owner(h, 1, 2) for h in range(2)] == [0, 1]
+assert [traceback_half_owner(h, 1, 8) for h in range(2)] == [0, 4]
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_traceback_gather_gloo():
+    """host side of the multi-GPU traceback on CPU (gloo, world_size 2): all-gather of the per-rank pieces and split
+    rows, their merge, and the ownership rule of the Hirschberg halves"""
+    import subprocess, sys, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "worker.py")
+        with open(path, "w") as f:
+            f.write(_TB_WORKER)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29641", path, ROOT],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("ok") == 2
