@@ -48,10 +48,6 @@ namespace anyseq {
 #ifndef ANYSEQ_CELL_FORM
 #define ANYSEQ_CELL_FORM 1
 #endif
-// steps before the end of a 32-row batch at which the next batch's border records are fetched (>= 32/R: at its start)
-#ifndef ANYSEQ_PREFETCH_LEAD
-#define ANYSEQ_PREFETCH_LEAD 3
-#endif
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * kWarp;
@@ -760,6 +756,12 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             PF_BEGIN();
             sm.in[lane] = make_int2(rec.x + go, rec.z);
             sm.q[r & QM] = MASK ? s_lut[qsym] : qsym;
+            // prefetch the next batch (its records may not be there yet: checked next time)
+            const int rn = r + 32;
+            if (rn < hb) {
+                rec = ld_record(lin + rn);
+                qsym = qrow[rn];
+            }
             __syncwarp();
             if constexpr (MASK) tile_mask(tb - lane, tm_cur);     // row group of this lane at step tb
             PF_END(pf_io);
@@ -767,31 +769,13 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         PF_BEGIN();
         // (3) B anti-diagonal steps; batches in which every row of every lane is
         //     inside the band run the unguarded body
-        //     The next batch's records are fetched speculatively kLead steps before the batch ends (checked at its
-        //     start): late enough that a left neighbour running at the minimal lag has published them, early enough to
-        //     hide the L2 round trip -- a lone warp per scheduler has nobody else to hide it behind.
-        constexpr int kLead = (ANYSEQ_PREFETCH_LEAD < B) ? ANYSEQ_PREFETCH_LEAD : B;
-        auto prefetch_next = [&]() {
-            const int rn = rb + lane + 32;
-            if (rn < hb) {
-                rec = ld_record(lin + rn);
-                qsym = qrow[rn];
-            }
-        };
         if (tb >= 31 && R * (tb + B) <= hb) {
 #pragma unroll 1
-            for (int t = tb; t < tb + B - kLead; ++t) step(std::false_type{}, t);
-            prefetch_next();
-#pragma unroll 1
-            for (int t = tb + B - kLead; t < tb + B; ++t) step(std::false_type{}, t);
+            for (int t = tb; t < tb + B; ++t) step(std::false_type{}, t);
         } else {
             const int tend = min(tb + B, T);
-            const int tmid = min(tb + B - kLead, tend);
 #pragma unroll 1
-            for (int t = tb; t < tmid; ++t) step(std::true_type{}, t);
-            if (rb < hb) prefetch_next();
-#pragma unroll 1
-            for (int t = tmid; t < tend; ++t) step(std::true_type{}, t);
+            for (int t = tb; t < tend; ++t) step(std::true_type{}, t);
         }
         PF_END(pf_steps);
     }
