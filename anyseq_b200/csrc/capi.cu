@@ -70,6 +70,7 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
         if (value <= 0) { anyseq::set_last_error("watchdog_ms must be > 0"); return ANYSEQ_ERR_BAD_ARG; }
         t.watchdog_ms = value;
     }
+    else if (n == "band_slack" && value >= 1) t.band_slack = value;
     else if (n == "force_generic") t.force_generic = value != 0;
     else if (n == "force_affine") t.force_affine = value != 0;
     else if (n == "local_end_cell") t.local_end_cell = value != 0;

@@ -49,7 +49,7 @@ struct Job {
     int h, w;
     int band_h;
     int nstrips, nbands;
-    long long item_begin;    // prefix sum of nstrips*nbands over jobs
+    long long item_begin;    // launch-wide index of the job's first strip (prefix sum of nstrips over the jobs of a launch)
     int4* col;
     int* rowH;
     int* rowF;

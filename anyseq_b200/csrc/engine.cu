@@ -369,43 +369,38 @@ int Engine::pick_K(int n, bool chained) const
     return 4;
 }
 
-// Band height.  Items are taken in index order by a window of `resident` warps,
-// i.e. `resident` consecutive strips of one band, each `lag` steps behind its
-// left neighbour (32 steps lane skew + the 32-row publish/fetch granularity).
-// All of them overlap only if a band is at least lag * window steps long;
-// bands are then equalised.
-int Engine::pick_band(int m, int nstrips, int resident, int K) const
+// Number of row bands of a launch.  Items are taken in index order (band, job, strip) by `resident` warps, i.e. by a
+// window of `resident` consecutive strips of one band, each `lag` rows behind its left neighbour (lane skew + the
+// 32-row publish and fetch batches).  When every strip of the launch has its own warp there is ONE band: a strip is
+// then relaxed top to bottom by one warp, and the distance to its left neighbour -- which drifts upwards as random
+// delays accumulate (measured: ~290 rows in the middle of a band for lone warps, against 105-136 at the start) --
+// costs nothing.  Otherwise a band must be high enough for the whole window to overlap with slack for that drift:
+// band_h = band_slack * lag * window; the price of higher bands is only the last, partially filled round of items.
+int Engine::plan_bands(int max_h, long long strips_total, int resident, int K) const
 {
-    if (tune.band_rows > 0) return std::max(32, std::min(m, (tune.band_rows + 31) / 32 * 32));
-    // rows a strip runs behind its left neighbour: lane skew (32 steps of R rows)
-    // plus the 32-row publish and fetch batches, plus slack
+    if (tune.band_rows > 0) {
+        const int bh = std::max(32, (tune.band_rows + 31) / 32 * 32);
+        return std::max(1, (max_h + bh - 1) / bh);
+    }
+    if (strips_total <= resident) return 1;
     const long long lag = 32LL * rows_per_step(K, use_mask_, track_) + 96;
-    const long long window = std::max(1, std::min(resident, nstrips));
-    long long target = std::max<long long>(lag * window, 4096);
-    if (target >= m) return std::max(32, (m + 31) / 32 * 32);
-    const long long nbands = (m + target - 1) / target;
-    long long bh = (m + nbands - 1) / nbands;
-    bh = (bh + 31) / 32 * 32;
-    return (int)bh;
+    const long long target = std::max<long long>(lag * resident * tune.band_slack, 4096);
+    return (int)std::max<long long>(1, (max_h + target - 1) / target);
 }
 
 // Launch init + strip kernels for a job list that is already in host memory.
 int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
-                     int* launches, bool interleave)
+                     int* launches)
 {
     const int njobs = (int)jobs.size();
-    long long total = 0;
+    long long strips_total = 0;
+    int max_h = 1;
     for (Job& j : jobs) {
-        j.item_begin = total;
-        total += (long long)j.nstrips * j.nbands;
+        j.item_begin = strips_total;           // launch-wide index of the job's first strip
+        strips_total += j.nstrips;
+        max_h = std::max(max_h, j.h);
     }
-    if (jobs_.ensure(sizeof(Job) * (size_t)njobs)) return ANYSEQ_ERR_NO_DEVICE;
-    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(jobs_.ptr, jobs.data(), sizeof(Job) * (size_t)njobs,
-                                      cudaMemcpyHostToDevice, stream_));
-    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
-#ifdef ANYSEQ_PROFILE
-    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
-#endif
+    if (strips_total > 0x7fffffff) { set_last_error("too many strips in one launch"); return ANYSEQ_ERR_UNSUPPORTED; }
 
     KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
@@ -413,10 +408,37 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
-    long long strips_total = 0;
-    for (const Job& j : jobs) strips_total += j.nstrips;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
     else nb = default_blocks_per_sm(K, use_mask_, track_, nb, strips_total, sm_count);
+    const int resident = nb * kWarpsPerBlock * sm_count;
+
+    // bands: the same number for every job of the launch (items are ordered band, job, strip)
+    const int nbands = plan_bands(max_h, strips_total, resident, K);
+    for (Job& j : jobs) {
+        const int bh = (j.h + nbands - 1) / nbands;
+        j.band_h = std::max(32, (bh + 31) / 32 * 32);
+        j.nbands = nbands;
+    }
+    const long long total = (long long)nbands * strips_total;
+
+    // jobs + the strip -> job table in one upload
+    const size_t jobs_bytes = (sizeof(Job) * (size_t)njobs + 255) / 256 * 256;
+    if (jobs_.ensure(jobs_bytes + sizeof(int) * (size_t)strips_total)) return ANYSEQ_ERR_NO_DEVICE;
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(jobs_.ptr, jobs.data(), sizeof(Job) * (size_t)njobs,
+                                      cudaMemcpyHostToDevice, stream_));
+    int* d_strip2job = reinterpret_cast<int*>(jobs_.as<uint8_t>() + jobs_bytes);
+    if (njobs > 1) {
+        strip2job_.resize((size_t)strips_total);
+        for (int j = 0; j < njobs; ++j)
+            std::fill(strip2job_.begin() + jobs[(size_t)j].item_begin, strip2job_.begin() + jobs[(size_t)j].item_begin + jobs[(size_t)j].nstrips, j);
+        ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(d_strip2job, strip2job_.data(), sizeof(int) * (size_t)strips_total,
+                                          cudaMemcpyHostToDevice, stream_));
+    }
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
+#ifdef ANYSEQ_PROFILE
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
+#endif
+
     long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
 
@@ -443,7 +465,8 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
         ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ka.next_item, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
     }
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
-    ka.interleave = interleave ? 1 : 0;
+    ka.strips_total = (int)strips_total;
+    ka.strip2job = d_strip2job;
     void* args[] = {&ka};
     ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, dyn_smem, stream_));
     if (launches) *launches += 2;
@@ -528,8 +551,6 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     const int K = want_edges_ ? 4 : pick_K(w, inbox != nullptr || next_inbox != nullptr);     // edge columns are wanted per 128-column block
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
-    const int resident = resident_warps(K, local, affine, nstrips);
-    const int band_h = pick_band(m, nstrips, resident, K);
 
     const size_t wpad = (size_t)nstrips * SW;
     if (col_.ensure(sizeof(int4) * (size_t)m) || rowH_.ensure(sizeof(int) * wpad) ||
@@ -543,9 +564,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     J.s = d_s_slice;
     J.h = m;
     J.w = w;
-    J.band_h = band_h;
-    J.nstrips = nstrips;
-    J.nbands = (m + band_h - 1) / band_h;
+    J.nstrips = nstrips;              // bands are planned by run_jobs
     J.col = col_.as<int4>();
     J.rowH = rowH_.as<int>();
     J.rowF = affine ? rowF_.as<int>() : nullptr;
@@ -677,10 +696,6 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
     const int K = pick_K((int)std::min<long long>((long long)w * npairs, 0x7fffffff), chained);
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
-    const long long strips_all = (long long)nstrips * npairs;
-    const int resident = resident_warps(K, local, affine, strips_all);
-    // the window of resident warps spans the strips of ALL pairs of a band
-    const int band_h = pick_band(m, (int)std::min<long long>(strips_all, 0x7fffffff), resident, K);
 
     // per-pair storage carved out of one buffer: col records, rowH, rowF, corner, progress, result words
     const size_t wpad = (size_t)nstrips * SW;
@@ -704,9 +719,7 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
         J.s = d_s_slice[p];
         J.h = m;
         J.w = w;
-        J.band_h = band_h;
         J.nstrips = nstrips;
-        J.nbands = (m + band_h - 1) / band_h;
         J.col = reinterpret_cast<int4*>(pb);
         J.rowH = reinterpret_cast<int*>(pb + b_col);
         J.rowF = affine ? reinterpret_cast<int*>(pb + b_col + b_row) : nullptr;
@@ -722,7 +735,7 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
     }
     int launches = 2 * npairs + 1;   // alphabet analysis
     init_col0_ = col_begin;
-    rc = run_jobs(jobs, sp, local, affine, K, &launches, /*interleave=*/true);
+    rc = run_jobs(jobs, sp, local, affine, K, &launches);
     init_col0_ = 0;
     if (rc) return rc;
     finish_score_kernel<<<npairs, 1024, 0, stream_>>>(jobs_.as<Job>(), sc.mode, col_begin, n_total, d_res);

@@ -41,6 +41,7 @@ struct Tuning {
     int band_rows = 0;       // 0 = auto
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
+    int band_slack = 2;      // band height = band_slack * lag * (resident warps) when the strips outnumber the warps
     bool force_generic = false;     // never use the MASK kernels (testing)
     bool force_affine = false;      // score path: run the Gotoh kernels even for gap_init == 0 (testing: must equal the linear kernels)
     bool local_end_cell = false;    // local scores also report the reference's end cell (single-row kernels)
@@ -142,11 +143,10 @@ public:
     void drop_host_batch_stream();       // batch_stream.cu: the cached pipeline of score_batch_host
 
 private:
-    int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
-                 int* launches, bool interleave = false);
+    int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K, int* launches);
     int pick_K(int n, bool chained = false) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
-    int pick_band(int m, int nstrips, int resident, int K) const;
+    int plan_bands(int max_h, long long strips_total, int resident, int K) const;
     int launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool affine, BatchArgs& ba, int max_long,
                      int max_short, cudaStream_t st);
 
@@ -165,6 +165,7 @@ private:
     cudaStream_t copy_stream_ = nullptr;                     // packed2 host pipeline: H2D of chunk c+1 under the kernel of chunk c
     cudaEvent_t p2_ready_[2] = {nullptr, nullptr}, p2_done_[2] = {nullptr, nullptr};
     int* h_misc_ = nullptr;           // pinned mirror of misc_
+    std::vector<int> strip2job_;      // run_jobs: launch-wide strip index -> job
     std::vector<int> last_splits_;    // split rows of the last traceback (slot -1 first)
     std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)
     int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)

@@ -66,8 +66,11 @@ struct KernelArgs {
     int* status;                    // [0] StatusCode, [1..3] diagnostics
     unsigned long long* next_item;  // work counter, initialised to the number of resident warps
     unsigned long long timeout_ns;  // watchdog for dependency waits
-    int interleave;                 // != 0: all jobs have the same nstrips / nbands and items are ordered
-                                    // (band, job, strip) instead of (job, band, strip): the jobs advance together
+    // Work items are ordered (band, job, strip): all jobs of a launch have the same NUMBER of bands (a short job's last
+    // bands may be empty) and advance together; strip2job maps a launch-wide strip index to its job, whose
+    // Job::item_begin is the launch-wide index of its first strip.
+    int strips_total;
+    const int* strip2job;
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -888,27 +891,20 @@ strip_kernel(const KernelArgs a)
     int jcur = 0;
     long long item = (long long)blockIdx.x * kWarpsPerBlock + warp;
     for (; item < a.total_items;) {
-        int band, strip;
-        if (a.interleave) {
-            const int ns = a.jobs[0].nstrips;
-            const long long per_band = (long long)a.njobs * ns;
-            band = (int)(item / per_band);
-            const int rem = (int)(item % per_band);
-            jcur = rem / ns;
-            strip = rem % ns;
-        } else {
-            while (jcur + 1 < a.njobs && item >= a.jobs[jcur + 1].item_begin) ++jcur;
-            const long long loc = item - a.jobs[jcur].item_begin;
-            band = (int)(loc / a.jobs[jcur].nstrips);
-            strip = (int)(loc % a.jobs[jcur].nstrips);
-        }
+        const int band = (int)(item / a.strips_total);
+        const int rem = (int)(item % a.strips_total);
+        jcur = a.njobs > 1 ? a.strip2job[rem] : 0;
+        const int strip = rem - (int)a.jobs[jcur].item_begin;
         const Job& J = a.jobs[jcur];
         const bool partial = (strip + 1) * SW > J.w;
-        bool ok;
-        if (partial)
+        bool ok = true;
+        if ((long long)band * J.band_h >= J.h) {
+            // a band past the end of a short job: nothing to relax
+        } else if (partial) {
             ok = process_item<LOCAL, AFFINE, K, true, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
-        else
+        } else {
             ok = process_item<LOCAL, AFFINE, K, false, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+        }
         if (!ok) return;
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(a.next_item, 1ull);

@@ -305,7 +305,6 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
         const int nparts = num_halfs / 2;
         const int K = std::max(4, std::min(Ktop, half / kWarp));
         const int SW = kWarp * K;
-        const int resident = resident_warps(K, local, false, (n + SW - 1) / SW);
 
         // sharded traceback: who relaxes which half of this level (TracebackShard)
         const int np_full = full_width / part_width;
@@ -338,8 +337,6 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
                 J.h = len;
                 J.w = w;
                 J.nstrips = (w + SW - 1) / SW;
-                J.band_h = pick_band(len, J.nstrips, resident, K);
-                J.nbands = (len + J.band_h - 1) / J.band_h;
                 J.col = (side == 0 ? col_.as<int4>() : col2_.as<int4>()) + off;
                 J.rowH = rowH_.as<int>() + c0;
                 J.corner = nullptr;   // patched below (offset into corner_/progress_)

@@ -316,7 +316,6 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
         const int nparts = num_halfs / 2;
         const int K = std::max(4, std::min(Ktop, half / kWarp));
         const int SW = kWarp * K;
-        const int resident = resident_warps(K, local, true, (n + SW - 1) / SW);
 
         // sharded traceback: who relaxes which half of this level (TracebackShard, traceback.cu)
         const int np_full = full_width / part_width;
@@ -351,8 +350,6 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
                 J.h = len;
                 J.w = w;
                 J.nstrips = (w + SW - 1) / SW;
-                J.band_h = pick_band(len, J.nstrips, resident, K);
-                J.nbands = (len + J.band_h - 1) / J.band_h;
                 J.col = (side == 0 ? col_.as<int4>() : col2_.as<int4>()) + off;
                 J.rowH = rowH_.as<int>() + c0;
                 J.rowF = rowF_.as<int>() + c0;

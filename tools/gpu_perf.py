@@ -29,6 +29,8 @@ def main():
         s = lut[torch.randint(0, 4, (n,), device="cuda", generator=g)]
     torch.cuda.synchronize()
     al = A.Aligner()
+    if os.environ.get("SLACK"):
+        al.set_option("band_slack", int(os.environ["SLACK"]))
     sch = A.affine_scoring_scheme() if affine else A.linear_scoring_scheme()
     for K in Ks:
         for band in bands:
