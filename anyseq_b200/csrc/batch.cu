@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, (K >= 32 ? 4 : (K >= 16 ? 5 : 6))) b
             int hr = 0, er = 0;
             int colbest = kScoreMin;     // semiglobal: max over H(i, n-1), kept by lane `outlane`
             StepState<1> st;
-            st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.tm[0] = 0u; st.qc = 0;
+            st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.xs = 0; st.tm[0] = 0u; st.qc = 0;
             auto row_mask = [&](int i) -> unsigned { return s_mask[(int)rq[i & 63] * 32 + lane]; };
             const int T = m + outlane;
             for (int tb = 0; tb < T; tb += 32) {

@@ -171,11 +171,20 @@ __global__ void local_end_cell_kernel(const unsigned long long* __restrict__ blo
 // ---------------------------------------------------------------------------
 using KernelFn = StripKernelFn;
 
-static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool track)
+static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool track, int form)
 {
     if (local && track) return affine ? get_strip_kernel_11t(K, mask) : get_strip_kernel_10t(K, mask);
-    if (local) return affine ? get_strip_kernel_11(K, mask) : get_strip_kernel_10(K, mask);
-    return affine ? get_strip_kernel_01(K, mask) : get_strip_kernel_00(K, mask);
+    if (local) return affine ? get_strip_kernel_11(K, mask, form) : get_strip_kernel_10(K, mask, form);
+    return affine ? get_strip_kernel_01(K, mask, form) : get_strip_kernel_00(K, mask, form);
+}
+
+// Cell form of a launch (strip_kernel.cuh): coupled cells need three warps per scheduler to fill the issue slots, which
+// only a launch with many more strips than warps can feed; everything else runs the decoupled cells, whose lone warps
+// are 1.5x faster (measured on a B200: 670 vs 1008 cycles per two-row step of a K = 32 strip).
+static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long long strips_total, int sm_count)
+{
+    if (tune.cell_form == 0 || tune.cell_form == 1) return (affine && mask && K >= 8) ? tune.cell_form : 1;
+    return (affine && mask && K >= 8 && strips_total >= 10LL * sm_count) ? 0 : 1;
 }
 
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)
@@ -190,13 +199,15 @@ static int rows_per_step(int K, bool mask, bool track)
 // than strips: at most one warp works on a strip at a time, the others would only
 // poll and add spread to the progress of the busy ones -- which is what the
 // strip-to-strip pipeline is sensitive to (measured: profiles/).
-static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max, long long nstrips, int sm_count)
+static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max, long long nstrips, int sm_count, int form)
 {
     int nb = occupancy_max;
     if (rows_per_step(K, mask, track) >= 2) {
         const long long per_round = 4LL * sm_count;              // warps of one CTA per SM
-        const int want = (int)std::max<long long>(1, (nstrips + per_round / 2) / per_round);
-        nb = std::min(nb, std::min(3, want));
+        // enough CTAs for every strip to have its own warp (single-band launches), at most what the cell form can use:
+        // the decoupled cells saturate the ALU pipe with two warps per scheduler, the coupled ones want three
+        const int want = (int)std::max<long long>(1, (nstrips + per_round - 1) / per_round);
+        nb = std::min(nb, std::min(form == 0 ? 3 : 2, want));
     }
     return nb;
 }
@@ -276,7 +287,7 @@ int Engine::init(int dev)
     ANYSEQ_CUDA_CHECK(cudaEventCreate(&ev0_));
     ANYSEQ_CUDA_CHECK(cudaEventCreate(&ev1_));
     if (misc_.ensure(sizeof(int) * kMiscWords)) return ANYSEQ_ERR_NO_DEVICE;
-    ANYSEQ_CUDA_CHECK(cudaMallocHost(&h_misc_, sizeof(int) * kMiscWords));
+    ANYSEQ_CUDA_CHECK(cudaMallocHost(&h_misc_, sizeof(int) * kMiscWords + 512));    // + the host-built byte -> code tables
     const char* env;
     if ((env = std::getenv("ANYSEQ_K"))) tune.cols_per_lane = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_BAND"))) tune.band_rows = std::atoi(env);
@@ -284,6 +295,7 @@ int Engine::init(int dev)
     if ((env = std::getenv("ANYSEQ_WATCHDOG_MS"))) tune.watchdog_ms = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_ALIGN_SCORE"))) tune.align_with_score = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_FORCE_GENERIC"))) tune.force_generic = std::atoi(env) != 0;
+    if ((env = std::getenv("ANYSEQ_CELL_FORM"))) tune.cell_form = std::atoi(env);
     if ((env = std::getenv("ANYSEQ_BATCH_PACKED"))) tune.batch_packed = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_LOCAL_END_CELL"))) tune.local_end_cell = std::atoi(env) != 0;
     return ANYSEQ_OK;
@@ -313,12 +325,12 @@ void Engine::destroy()
 
 int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
-    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, pick_form(tune, affine, use_mask_, K, nstrips, sm_count));
     if (!fn) return 0;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, track_, ncodes_, K)) != cudaSuccess) return 0;
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, nstrips, sm_count);
+    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, nstrips, sm_count, pick_form(tune, affine, use_mask_, K, nstrips, sm_count));
     return nb * kWarpsPerBlock * sm_count;
 }
 
@@ -326,6 +338,7 @@ int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 // that is resident in device memory; builds the byte -> code tables.
 int Engine::analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n)
 {
+    if (alphabet_ready_) { alphabet_ready_ = false; return ANYSEQ_OK; }     // done on the host for this very pair
     if (lut_.ensure(512 + 64 + 16)) return ANYSEQ_ERR_NO_DEVICE;
     unsigned* bits = reinterpret_cast<unsigned*>(lut_.as<uint8_t>() + 512);   // [16] presence, then ncodes
     int* d_ncodes = reinterpret_cast<int*>(bits + 16);
@@ -341,6 +354,31 @@ int Engine::analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s
     ncodes_ = h_misc_[kMiscWords - 1];
     use_mask_ = ncodes_ <= kMaxCodes && !tune.force_generic;
     if (!use_mask_) ncodes_ = 1;
+    return ANYSEQ_OK;
+}
+
+// The same analysis for sequences that are still in HOST memory (score_host / align_host): a pass over the bytes on the
+// CPU and one small upload instead of three kernels and a device -> host round trip -- which is most of the fixed cost
+// of a small alignment (align -r 10000: ~50 us of 1.5 ms).  The next analyse_alphabet() call is then skipped.
+int Engine::analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* s, long long n)
+{
+    if (lut_.ensure(512 + 64 + 16)) return ANYSEQ_ERR_NO_DEVICE;
+    bool in_q[256] = {false}, in_s[256] = {false};
+    for (long long i = 0; i < m; ++i) in_q[q[i]] = true;
+    for (long long j = 0; j < n; ++j) in_s[s[j]] = true;
+    uint8_t* lut = reinterpret_cast<uint8_t*>(h_misc_ + kMiscWords);     // pinned scratch behind the misc mirror
+    int next = 1;
+    for (int b = 0; b < 256; ++b) {
+        int code = 0;
+        if (in_q[b] && in_s[b]) { code = next < 255 ? next : 255; ++next; }
+        lut[b] = (uint8_t)code;
+        lut[256 + b] = (uint8_t)code;
+    }
+    ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(lut_.ptr, lut, 512, cudaMemcpyHostToDevice, stream_));
+    ncodes_ = next;
+    use_mask_ = ncodes_ <= kMaxCodes && !tune.force_generic;
+    if (!use_mask_) ncodes_ = 1;
+    alphabet_ready_ = true;
     return ANYSEQ_OK;
 }
 
@@ -402,14 +440,15 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     }
     if (strips_total > 0x7fffffff) { set_last_error("too many strips in one launch"); return ANYSEQ_ERR_UNSUPPORTED; }
 
-    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local);
+    const int form = pick_form(tune, affine, use_mask_, K, strips_total, sm_count);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
     const size_t dyn_smem = mask_smem_bytes(use_mask_, track_, ncodes_, K);
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, strips_total, sm_count);
+    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, strips_total, sm_count, form);
     const int resident = nb * kWarpsPerBlock * sm_count;
 
     // bands: the same number for every job of the launch (items are ordered band, job, strip)
@@ -588,6 +627,7 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     // the tag of a run is agreed without communication: both ends count their uses of the inbox
     if (inbox) { J.in = inbox->records; J.in_tag = 0x40000000 + (++inbox->uses_in & 0xffffff); }
     if (next_inbox) { J.out = next_inbox->records; J.out_tag = 0x40000000 + (++next_inbox->uses_out & 0xffffff); }
+    J.edge_e = (next_inbox != nullptr || want_edges_) ? 1 : 0;     // who reads E of a ragged last strip's edge column
 
     std::vector<Job> jobs(1, J);
     int launches = 0;
@@ -732,6 +772,7 @@ int Engine::score_strip_device_multi(const anyseq_scoring& sc, int npairs, const
         Inbox* nx = next_inbox ? next_inbox[p] : nullptr;
         if (in) { J.in = in->records; J.in_tag = 0x40000000 + (++in->uses_in & 0xffffff); }
         if (nx) { J.out = nx->records; J.out_tag = 0x40000000 + (++nx->uses_out & 0xffffff); }
+        J.edge_e = nx ? 1 : 0;
     }
     int launches = 2 * npairs + 1;   // alphabet analysis
     init_col0_ = col_begin;
@@ -796,7 +837,13 @@ int Engine::score_host(const anyseq_scoring& sc, const char* q, int m, const cha
     // sequence_to_device: src/mapping_acc.impala:125-131
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_q_.ptr, q, (size_t)m, cudaMemcpyHostToDevice, stream_));
     ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(seq_s_.ptr, s, (size_t)n, cudaMemcpyHostToDevice, stream_));
-    return score_device(sc, seq_q_.as<uint8_t>(), m, seq_s_.as<uint8_t>(), n, out);
+    if ((long long)m + n <= kHostAlphabetLimit) {
+        const int rc = analyse_alphabet_host(reinterpret_cast<const uint8_t*>(q), m, reinterpret_cast<const uint8_t*>(s), n);
+        if (rc) return rc;
+    }
+    const int rc = score_device(sc, seq_q_.as<uint8_t>(), m, seq_s_.as<uint8_t>(), n, out);
+    alphabet_ready_ = false;
+    return rc;
 }
 
 }  // namespace anyseq

@@ -41,6 +41,7 @@ struct Tuning {
     int band_rows = 0;       // 0 = auto
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int watchdog_ms = 20000;
+    int cell_form = -1;      // -1 = per launch (engine.cu: pick_form), 0 = coupled, 1 = decoupled cells
     int band_slack = 2;      // band height = band_slack * lag * (resident warps) when the strips outnumber the warps
     bool force_generic = false;     // never use the MASK kernels (testing)
     bool force_affine = false;      // score path: run the Gotoh kernels even for gap_init == 0 (testing: must equal the linear kernels)
@@ -146,6 +147,7 @@ private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K, int* launches);
     int pick_K(int n, bool chained = false) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
+    int analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* s, long long n);
     int plan_bands(int max_h, long long strips_total, int resident, int K) const;
     int launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool affine, BatchArgs& ba, int max_long,
                      int max_short, cudaStream_t st);
@@ -170,6 +172,8 @@ private:
     std::vector<int> last_types_;     // Gotoh traceback: vertex types of the split rows (0 = H, 1 = E)
     int ncodes_ = 1;                  // alphabet codes of the current pair (MASK kernels)
     bool use_mask_ = false;
+    bool alphabet_ready_ = false;     // the tables of the pair about to be relaxed were built on the host
+    static constexpr long long kHostAlphabetLimit = 8 << 20;     // host-side alphabet pass up to this many symbols
     void* host_batch_stream_ = nullptr;  // BatchStream* reused by score_batch_host
     bool want_edges_ = false;    // the running score call keeps the strips' edge columns (K = 4)
     bool force_track_ = false;   // ... and tracks the local end cell whatever the option says

@@ -6,7 +6,11 @@
 
 namespace anyseq {
 
+#ifdef ANYSEQ_INST_TRACK
 StripKernelFn ANYSEQ_INST_NAME(int K, bool mask)
+#else
+StripKernelFn ANYSEQ_INST_NAME(int K, bool mask, int form)
+#endif
 {
     constexpr bool L = ANYSEQ_INST_LOCAL;
     constexpr bool A = ANYSEQ_INST_AFFINE;
@@ -27,6 +31,16 @@ StripKernelFn ANYSEQ_INST_NAME(int K, bool mask)
         default: return nullptr;
     }
 #else
+    if constexpr (ANYSEQ_INST_AFFINE) {
+        if (mask && form == 0) {          // coupled cells: Gotoh, small alphabets (the full-width workhorse)
+            switch (K) {
+                case 8: return strip_kernel<L, A, 8, true, false, 0>;
+                case 16: return strip_kernel<L, A, 16, true, false, 0>;
+                case 32: return strip_kernel<L, A, 32, true, false, 0>;
+                default: break;
+            }
+        }
+    }
     if (mask) {
         switch (K) {
             case 4: return strip_kernel<L, A, 4, true>;

@@ -45,9 +45,9 @@ namespace anyseq {
 //                   win the maximum that forms E(i,j) (E+go <= E+ge).  A lone warp saturates its scheduler's ALU pipe, so
 //                   half as many (twice as fast) warps are needed -- which is what the strip-to-strip chain, narrow
 //                   problems and multi-GPU slices are sensitive to.
-#ifndef ANYSEQ_CELL_FORM
-#define ANYSEQ_CELL_FORM 1
-#endif
+// Both forms are built (template parameter FORM of strip_kernel); engine.cu picks per launch: the coupled form where
+// three warps per scheduler can be fed (Gotoh, strips >> warps: 3.71 vs 3.52 TCUPS on the 4.6 Mbp pair), the decoupled
+// form everywhere else (linear gaps, single-band launches, small problems, multi-GPU slices).
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * kWarp;
@@ -127,6 +127,17 @@ __device__ __forceinline__ int diag_plus_sigma_mask(unsigned mask, int d, int on
         : "=&r"(dd)
         : "r"(mask), "n"(1u << C), "r"(d), "r"(one), "r"(diff), "r"(same));
     return dd;
+}
+
+// dst = src if bit C of `mask` is set -- as a predicated IMAD (FMA pipe) whose predicate ptxas takes from R2P, like the
+// match bits above.  Ragged strips use it to keep the edge column's values: 1/7 ALU instruction per cell instead of
+// ISETP + SEL per cell.
+template <int C>
+__device__ __forceinline__ void capture_if_bit(unsigned mask, int& dst, int src, int one)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t@p mad.lo.s32 %0, %3, %4, 0;\n\t}"
+        : "+r"(dst)
+        : "r"(mask), "n"(1u << C), "r"(src), "r"(one));
 }
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p)
@@ -215,6 +226,7 @@ struct StepState {
     int best;        // LOCAL: running maximum
     int hprev;       // LOCAL: H of the previous (even) column, folded pairwise with VIMNMX3
     int es;          // PARTIAL: E of the edge column
+    int xs;          // PARTIAL: X of the edge column
     int bpos;        // TRACK: row * K + column (within the item, within the lane) of the first cell attaining best
     int rowpos;      // TRACK: row * K of the row being relaxed
     unsigned tm[W];  // MASK: tile mask of the lane's current row group
@@ -224,6 +236,7 @@ struct StepState {
 struct StepConst {
     int one, ge, go, diff_o, same_o;
     int nvalid, outc;   // PARTIAL only
+    unsigned capmask;   // PARTIAL only: bit outc
 };
 
 template <int BASE, int W>
@@ -247,7 +260,7 @@ __device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int
 // RS / RO: the row is row RO of an RS-row group (selects its bits in the tile mask).
 // TRACK (local scheme, single-row kernels): also remember WHERE the lane's maximum was first reached, in the
 // lane's own row-major order (strict '>'), for the reference's end-cell rule (src/scoring_cpu.impala:48-72).
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int RS, int RO, int C, bool TRACK = false, int FORM = 0>
+template <bool LOCAL, bool AFFINE, int K, int PARTIAL, bool MASK, int RS, int RO, int C, bool TRACK = false, int FORM = 0>
 struct Cell {
     template <int KF, int KS, int W>
     static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepState<W>& s,
@@ -270,9 +283,7 @@ struct Cell {
                 if constexpr (LOCAL) mp = __vimax3_s32(imad_add(f, k.one, k.go), dd, k.go);   // H >= 0  <=>  X >= go
                 else mp = __viaddmax_s32(f, k.go, dd);
                 s.e = __viaddmax_s32(s.e, k.ge, s.xleft);
-                if constexpr (PARTIAL) {
-                    if (C == k.outc) s.es = s.e;
-                }
+                if constexpr (PARTIAL != 0) capture_if_bit<C>(k.capmask, s.es, s.e, k.one);
                 x = __viaddmax_s32(s.e, k.go, mp);
                 F[C] = f;
                 s.xleft = (C + 1 < K) ? mp : x;        // the lane hands X (not M) to its right neighbour
@@ -291,15 +302,14 @@ struct Cell {
                 }
             }
             X[C] = x;
+            if constexpr (PARTIAL != 0) capture_if_bit<C>(k.capmask, s.xs, x, k.one);
             if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK, FORM>::run(X, F, sc, s, k);
             return;
         }
         int h;
         if constexpr (AFFINE) {
             s.e = __viaddmax_s32(s.e, k.ge, s.xleft);
-            if constexpr (PARTIAL) {
-                if (C == k.outc) s.es = s.e;
-            }
+            if constexpr (PARTIAL != 0) capture_if_bit<C>(k.capmask, s.es, s.e, k.one);
             const int f = __viaddmax_s32(F[C], k.ge, up);
             h = LOCAL ? __vimax3_s32_relu(dd, s.e, f) : __vimax3_s32(dd, s.e, f);
             F[C] = f;
@@ -321,6 +331,7 @@ struct Cell {
         const int x = AFFINE ? imad_add(h, k.one, k.go) : h;
         X[C] = x;
         s.xleft = x;
+        if constexpr (PARTIAL != 0) capture_if_bit<C>(k.capmask, s.xs, x, k.one);
         if constexpr (C + 1 < K) Cell<LOCAL, AFFINE, K, PARTIAL, MASK, RS, RO, C + 1, TRACK, FORM>::run(X, F, sc, s, k);
     }
 };
@@ -342,7 +353,7 @@ struct StepStateR {
     int xs[R], es[R];    // PARTIAL: X and E of the edge column, per row
 };
 
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, int C, int FORM = 0>
+template <bool LOCAL, bool AFFINE, int K, int PARTIAL, bool MASK, int R, int C, int FORM = 0>
 struct CellR {
     template <int KF, int KS, int W>
     static __device__ __forceinline__ void run(int (&X)[K], int (&F)[KF], const int (&sc)[KS], StepStateR<R, W>& s,
@@ -374,8 +385,9 @@ struct CellR {
                 hrow[r] = h;
                 s.x[r] = (C + 1 < K) ? mp : x;
                 above_x = x;
-                if constexpr (PARTIAL) {
-                    if (C == k.outc) { s.xs[r] = x; s.es[r] = s.e[r]; }
+                if constexpr (PARTIAL != 0) {
+                    capture_if_bit<C>(k.capmask, s.xs[r], x, k.one);
+                    capture_if_bit<C>(k.capmask, s.es[r], s.e[r], k.one);
                 }
                 continue;
             } else if constexpr (FORM == 1) {
@@ -396,8 +408,9 @@ struct CellR {
             hrow[r] = h;
             s.x[r] = x;
             above_x = x;
-            if constexpr (PARTIAL) {
-                if (C == k.outc) { s.xs[r] = x; s.es[r] = s.e[r]; }   // E of the last column: Gotoh traceback joins
+            if constexpr (PARTIAL != 0) {
+                capture_if_bit<C>(k.capmask, s.xs[r], x, k.one);
+                if constexpr (AFFINE) capture_if_bit<C>(k.capmask, s.es[r], s.e[r], k.one);   // E of the last column: Gotoh traceback joins
             }
         }
         if constexpr (LOCAL) {
@@ -439,12 +452,12 @@ __device__ __forceinline__ void st_record(int4* p, int4 v)
                  : "memory");
 }
 
-// One (band, strip) item.  PARTIAL = the strip is cut by the right matrix edge
+// One (band, strip) item.  PARTIAL != 0: the strip is cut by the right matrix edge
 // (only the last strip of a job can be): the columns past the edge compute
 // don't-care values (dependencies only run left->right, so they never reach a
 // valid cell), the edge column is picked out for the output, and the local
 // maximum is masked.  R = rows per lane and step (PARTIAL items use R = 1).
-template <bool LOCAL, bool AFFINE, int K, bool PARTIAL, bool MASK, int R, bool TRACK = false>
+template <bool LOCAL, bool AFFINE, int K, int PARTIAL, bool MASK, int R, bool TRACK = false, int FORM_SEL = 1>
 __device__ __forceinline__ bool process_item(const Job& J, const int band, const int strip,
                                              const KernelArgs& a, WarpSmem& sm,
                                              unsigned* __restrict__ s_mask /* [ncodes][32][W] spread column masks */,
@@ -457,7 +470,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     constexpr int B = 32 / R;              // steps per batch (a batch = 32 rows)
     constexpr int QM = 64 * R - 1;         // query ring mask
     constexpr int W = TileWords<R, K>::value;
-    constexpr int FORM = TRACK ? 0 : ANYSEQ_CELL_FORM;     // the end-cell tracking kernels keep the coupled form (they need H itself)
+    constexpr int FORM = TRACK ? 0 : FORM_SEL;     // the end-cell tracking kernels keep the coupled form (they need H itself)
     const int i0 = band * J.band_h;
     const int hb = min(J.band_h, J.h - i0);
     const int j0 = strip * SW;
@@ -534,6 +547,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     const int outlane = PARTIAL ? (wv - 1) / K : 31;
     k.outc = PARTIAL ? (wv - 1) % K : K - 1;
     k.nvalid = PARTIAL ? max(0, min(K, wv - lane * K)) : K;
+    k.capmask = PARTIAL ? (1u << k.outc) : 0u;
     const int ngroups = (hb + R - 1) / R;  // row groups of R rows
     const int T = ngroups + outlane;       // number of steps
     int hr[R], er[R];
@@ -544,7 +558,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     for (int w = 0; w < W; ++w) tm_cur[w] = 0u;
     int flushed = 0;                       // rows published so far
     StepState<W> st;
-    st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.qc = 0;
+    st.dd = 0; st.e = 0; st.xleft = 0; st.best = kScoreMin; st.hprev = kScoreMin; st.es = 0; st.xs = 0; st.qc = 0;
     st.bpos = 0; st.rowpos = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) st.tm[w] = 0u;
@@ -607,14 +621,8 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK, FORM>::run(X, F, sc, st, k);
         hro = st.xleft;
         ero = st.e;
-        if constexpr (PARTIAL) {
-            if (lane == outlane) {
-                int hs = X[0];
-#pragma unroll
-                for (int c = 1; c < K; ++c)
-                    if (c == k.outc) hs = X[c];
-                sm.out[row & 63] = make_int2(hs, st.es);
-            }
+        if constexpr (PARTIAL != 0) {
+            if (lane == outlane) sm.out[row & 63] = make_int2(st.xs, st.es);
         } else {
             if (lane == 31) sm.out[row & 63] = make_int2(hro, ero);
         }
@@ -676,8 +684,8 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
             if (lane == outlane) {
 #pragma unroll
                 for (int r = 0; r < R; r += 2) {
-                    const int4 v = PARTIAL ? make_int4(s2.xs[r], s2.es[r], s2.xs[r + 1], s2.es[r + 1])
-                                           : make_int4(hr[r], er[r], hr[r + 1], er[r + 1]);
+                    const int4 v = PARTIAL != 0 ? make_int4(s2.xs[r], s2.es[r], s2.xs[r + 1], s2.es[r + 1])
+                                                : make_int4(hr[r], er[r], hr[r + 1], er[r + 1]);
                     *reinterpret_cast<int4*>(&sm.out[(R * g + r) & 63]) = v;
                 }
             }
@@ -840,7 +848,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
 #define ANYSEQ_ROWS_K8 4     // narrow problems have few strips: four chains per warp make the lone warps fast
 #endif
 #ifndef ANYSEQ_ROWS_K4
-#define ANYSEQ_ROWS_K4 1
+#define ANYSEQ_ROWS_K4 2     // small problems are latency-bound: two rows per step cost 123 instead of 2 x 107 cycles (SASS issue model)
 #endif
 template <int K, bool MASK>
 struct StripRows {
@@ -860,7 +868,7 @@ constexpr int strip_min_blocks()
     return K >= 32 ? 4 : (K >= 16 ? 5 : 6);
 }
 
-template <bool LOCAL, bool AFFINE, int K, bool MASK, bool TRACK = false>
+template <bool LOCAL, bool AFFINE, int K, bool MASK, bool TRACK = false, int FORM = 1>
 __global__ void __launch_bounds__(kThreads, TRACK ? (K >= 32 ? 4 : (K >= 16 ? 5 : 6)) : strip_min_blocks<K, MASK>())
 strip_kernel(const KernelArgs a)
 {
@@ -901,9 +909,9 @@ strip_kernel(const KernelArgs a)
         if ((long long)band * J.band_h >= J.h) {
             // a band past the end of a short job: nothing to relax
         } else if (partial) {
-            ok = process_item<LOCAL, AFFINE, K, true, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, 1, MASK, R, TRACK, FORM>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         } else {
-            ok = process_item<LOCAL, AFFINE, K, false, MASK, R, TRACK>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
+            ok = process_item<LOCAL, AFFINE, K, 0, MASK, R, TRACK, FORM>(J, band, strip, a, s_warp[warp], s_mask, s_lut, lane);
         }
         if (!ok) return;
         unsigned long long nxt = 0;
@@ -914,10 +922,11 @@ strip_kernel(const KernelArgs a)
 
 using StripKernelFn = void (*)(const KernelArgs);
 // defined in strip_inst_*.cu (one translation unit per (LOCAL, AFFINE) pair)
-StripKernelFn get_strip_kernel_00(int K, bool mask);
-StripKernelFn get_strip_kernel_01(int K, bool mask);
-StripKernelFn get_strip_kernel_10(int K, bool mask);
-StripKernelFn get_strip_kernel_11(int K, bool mask);
+// form: 0 = coupled, 1 = decoupled cells; the coupled form exists for the Gotoh MASK kernels only
+StripKernelFn get_strip_kernel_00(int K, bool mask, int form);
+StripKernelFn get_strip_kernel_01(int K, bool mask, int form);
+StripKernelFn get_strip_kernel_10(int K, bool mask, int form);
+StripKernelFn get_strip_kernel_11(int K, bool mask, int form);
 StripKernelFn get_strip_kernel_10t(int K, bool mask);   // local + end-cell tracking
 StripKernelFn get_strip_kernel_11t(int K, bool mask);
 

@@ -358,6 +358,7 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
                 J.best = misc_.as<int>() + kMiscBest;
                 J.init_global = glob;
                 J.top_open = (side == 0 ? hp.open_l : hp.open_r) + ge;
+                J.edge_e = 1;            // the E-type joins of hb_sum read E of every half's last column
                 jobs.push_back(J);
             }
         }

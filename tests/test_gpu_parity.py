@@ -945,3 +945,25 @@ def test_sharded_traceback_equals_single_gpu(oracle):
         finally:
             for a in als:
                 a.close()
+
+
+def test_full_size_c3_affine_traceback_against_cpu(aligner):
+    """BASELINE.json configs[2] as written: LOCAL, AFFINE, linear-space traceback of the random 1 Mbp pair (seeds 1/2),
+    against the frozen result of the restated CPU path (tools/freeze_fullsize.py c3affine, 38 min on 6 cores):
+    alignment strings, split rows and vertex types, compared as sha256"""
+    import json
+    import anyseq_b200 as A
+    from anyseq_b200 import workloads as W
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")
+    gold = json.load(open(path)).get("c3affine_local")
+    if gold is None:
+        pytest.skip("tests/golden/fullsize.json has no full-size C3 entry yet")
+    q, s = W.random_pair(gold["m"], gold["n"], *gold["seeds"])
+    aligner.set_option("align_with_score", 0)
+    try:
+        r = aligner.align("local", q, s, A.affine_scoring_scheme(*gold["scheme"]))
+    finally:
+        aligner.set_option("align_with_score", 1)
+    assert _sha(r.aligned_query, r.aligned_subject) == gold["sha"]
+    assert hashlib.sha256(np.asarray(aligner.last_splits(), dtype=np.int32).tobytes()).hexdigest()[:16] == gold["splits_sha"]
+    assert hashlib.sha256(np.asarray(aligner.last_split_types(), dtype=np.int32).tobytes()).hexdigest()[:16] == gold["types_sha"]

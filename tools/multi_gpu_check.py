@@ -53,6 +53,53 @@ for launch in range(3):
     assert got == [want, want2, want, want2][: 4 - launch], (launch, got, want, want2)
 wave.close()
 dist.barrier()
+
+# (4) end cells of the combined ranks == single GPU, host-buffer strip entry (anyseq_score_strip)
+wave = StripWavefront(al, rank, world, m, dist, depth=1)
+wave.reset()
+for mode in ("global", "semiglobal", "local"):
+    one = al.score(mode, q, s, sch)
+    dist.barrier()
+    p = wave.run_host(mode, sch, q, np.ascontiguousarray(s[c0:c1]), c0, c1, n)
+    r = wave.combine(mode, sch, p)
+    assert (r.score, r.end_i, r.end_j) == (one.score, one.end_i, one.end_j), (mode, (r.score, r.end_i, r.end_j), (one.score, one.end_i, one.end_j))
+wave.close()
+
+# (5) multi-GPU linear-space traceback (anyseq_align_sharded, world a power of two): bit-identical strings and splits,
+#     linear and Gotoh gaps; timing at the size given by TB_N (default 200 kbp; 1000000 = BASELINE configs[2], checked
+#     against the frozen CPU sha of tests/golden/fullsize.json)
+import hashlib, json, time
+from anyseq_b200.multigpu import ShardedTraceback
+if world & (world - 1) == 0:
+    tb_n = int(os.environ.get("TB_N", "200000"))
+    tq, ts = W.random_pair(tb_n, tb_n, 1, 2)
+    st = ShardedTraceback(al, rank, world, dist)
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "fullsize.json")))
+    al.set_option("align_with_score", 0)
+    for name, mode, tsch in (("linear", "local", A.linear_scoring_scheme()), ("affine", "local", A.affine_scoring_scheme()),
+                             ("affine", "global", A.affine_scoring_scheme())):
+        st.align(mode, tq[:20000], ts[:20000], tsch)                       # warm-up
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        piece = st.align(mode, tq, ts, tsch)
+        aq, as_, splits = st.gather(tb_n, tb_n, piece)
+        dist.barrier()
+        t_multi = time.perf_counter() - t0
+        sha = hashlib.sha256(aq + b"\n" + as_).hexdigest()[:16]
+        if rank == 0:
+            t0 = time.perf_counter()
+            one = al.align(mode, tq, ts, tsch)
+            t_one = time.perf_counter() - t0
+            same = (aq, as_) == (one.aligned_query, one.aligned_subject) and splits == al.last_splits()
+            g = gold.get("c3affine_local") if (name == "affine" and mode == "local" and tb_n == 1000000) else None
+            print(f"sharded traceback {name} {mode} {tb_n} x {tb_n}: {world} GPUs {t_multi*1e3:.1f} ms, 1 GPU {t_one*1e3:.1f} ms "
+                  f"(x{t_one/t_multi:.2f}), identical={same}, sha={sha}" + (f", frozen CPU sha equal={sha == g['sha']}" if g else ""), flush=True)
+            assert same
+            if g:
+                assert sha == g["sha"]
+        dist.barrier()
+    al.set_option("align_with_score", 1)
+
 if rank == 0:
     print(f"multi-GPU check ok on {world} GPUs: batch of {len(ref)} pairs, wavefront {m} x {n} score {want}")
 dist.destroy_process_group()
