@@ -213,11 +213,26 @@ static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max
 }
 
 // dynamic shared memory of the MASK kernels: [warps][ncodes][32 lanes][W words] spread column masks
-static size_t mask_smem_bytes(bool mask, bool track, int ncodes, int K)
+static size_t mask_smem_bytes(bool mask, bool track, int ncodes, int K, int warps)
 {
     if (!mask) return 0;
     const int words = std::max(1, rows_per_step(K, mask, track) * K / 32);
-    return sizeof(unsigned) * 32 * (size_t)ncodes * kWarpsPerBlock * words;
+    return sizeof(unsigned) * 32 * (size_t)ncodes * warps * words;
+}
+
+// Launch shape of a strip kernel: the end-cell tracking kernels run `nb` CTAs of 4 warps per SM, all others ONE CTA of
+// 4 * nb warps per SM (strip_kernel.cuh: the warps of a scheduler take adjacent strips).  Returns the largest nb <= want
+// that fits, 0 if none does.
+static int fit_blocks_per_sm(KernelFn fn, bool track, bool mask, int ncodes, int K, int want)
+{
+    for (int nb = want; nb >= 1; --nb) {
+        int got = 0;
+        const int warps = track ? kWarpsPerBlock : kWarpsPerBlock * nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, fn, warps * kWarp, mask_smem_bytes(mask, track, ncodes, K, warps)) != cudaSuccess)
+            return 0;
+        if (track ? got >= nb : got >= 1) return nb;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -325,13 +340,13 @@ void Engine::destroy()
 
 int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
-    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, pick_form(tune, affine, use_mask_, K, nstrips, sm_count));
+    const int form = pick_form(tune, affine, use_mask_, K, nstrips, sm_count);
+    KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) return 0;
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, mask_smem_bytes(use_mask_, track_, ncodes_, K)) != cudaSuccess) return 0;
-    if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, nstrips, sm_count, pick_form(tune, affine, use_mask_, K, nstrips, sm_count));
-    return nb * kWarpsPerBlock * sm_count;
+    const bool track = track_ && local;
+    int want = tune.blocks_per_sm > 0 ? tune.blocks_per_sm : default_blocks_per_sm(K, use_mask_, track, track ? 6 : 3, nstrips, sm_count, form);
+    if (!track) want = std::min(want, kMaxStripWarps / kWarpsPerBlock);
+    return fit_blocks_per_sm(fn, track, use_mask_, ncodes_, K, want) * kWarpsPerBlock * sm_count;
 }
 
 // Decide between the MASK and the generic kernels for a (query, subject) pair
@@ -380,6 +395,19 @@ int Engine::analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* 
     if (!use_mask_) ncodes_ = 1;
     alphabet_ready_ = true;
     return ANYSEQ_OK;
+}
+
+// Strip width for launches whose jobs advance together (Hirschberg levels: all halves of a level, `n` columns in
+// total): the widest strips that still give every scheduler a warp -- measured on the 1 Mbp traceback, K = 32 against
+// K = 16 per level: 140 vs 170 ms, 68 vs 78, 34.5 vs 38, 17.5 vs 20.
+int Engine::pick_K_levels(int n_total) const
+{
+    if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 || tune.cols_per_lane == 32)
+        return tune.cols_per_lane;
+    const long long want = 4LL * sm_count;             // one warp per scheduler
+    for (int K = use_mask_ ? 32 : 16; K > 4; K /= 2)
+        if ((long long)n_total / (kWarp * K) >= want) return K;
+    return 4;
 }
 
 int Engine::pick_K(int n, bool chained) const
@@ -443,12 +471,13 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     const int form = pick_form(tune, affine, use_mask_, K, strips_total, sm_count);
     KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
-    const size_t dyn_smem = mask_smem_bytes(use_mask_, track_, ncodes_, K);
-    int nb = 0;
-    ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn_smem));
+    const bool track = track_ && local;
+    int want = tune.blocks_per_sm > 0 ? tune.blocks_per_sm : default_blocks_per_sm(K, use_mask_, track, track ? 6 : 3, strips_total, sm_count, form);
+    if (!track) want = std::min(want, kMaxStripWarps / kWarpsPerBlock);
+    const int nb = fit_blocks_per_sm(fn, track, use_mask_, ncodes_, K, want);
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
-    if (tune.blocks_per_sm > 0) nb = std::min(nb, tune.blocks_per_sm);
-    else nb = default_blocks_per_sm(K, use_mask_, track_, nb, strips_total, sm_count, form);
+    const int wpb = track ? kWarpsPerBlock : kWarpsPerBlock * nb;          // warps per CTA
+    const int ctas_per_sm = track ? nb : 1;
     const int resident = nb * kWarpsPerBlock * sm_count;
 
     // bands: the same number for every job of the launch (items are ordered band, job, strip)
@@ -478,8 +507,10 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
 #endif
 
-    long long want_blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int grid = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>(want_blocks, 1));
+    // few items: spread them over the SMs with 4-warp CTAs (one warp per scheduler) before doubling up
+    const int wpb_used = (total <= (long long)kWarpsPerBlock * sm_count) ? kWarpsPerBlock : wpb;
+    long long want_blocks = (total + wpb_used - 1) / wpb_used;
+    int grid = (int)std::min<long long>((long long)ctas_per_sm * sm_count, std::max<long long>(want_blocks, 1));
 
     {
         int maxlen = 1;
@@ -500,14 +531,15 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ka.status = misc_.as<int>() + kMiscStatus;
     ka.next_item = reinterpret_cast<unsigned long long*>(misc_.as<int>() + kMiscCounter);
     {
-        const unsigned long long first = (unsigned long long)grid * kWarpsPerBlock;
+        const unsigned long long first = (unsigned long long)grid * wpb_used;
         ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ka.next_item, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
     }
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
     ka.strips_total = (int)strips_total;
     ka.strip2job = d_strip2job;
     void* args[] = {&ka};
-    ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(kThreads), args, dyn_smem, stream_));
+    ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(wpb_used * kWarp), args,
+                                                  mask_smem_bytes(use_mask_, track, ncodes_, K, wpb_used), stream_));
     if (launches) *launches += 2;
     return ANYSEQ_OK;
 }

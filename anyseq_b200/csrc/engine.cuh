@@ -146,6 +146,7 @@ public:
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K, int* launches);
     int pick_K(int n, bool chained = false) const;
+    int pick_K_levels(int n_total) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* s, long long n);
     int plan_bands(int max_h, long long strips_total, int resident, int K) const;

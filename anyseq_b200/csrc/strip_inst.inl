@@ -31,16 +31,18 @@ StripKernelFn ANYSEQ_INST_NAME(int K, bool mask, int form)
         default: return nullptr;
     }
 #else
-    if constexpr (ANYSEQ_INST_AFFINE) {
-        if (mask && form == 0) {          // coupled cells: Gotoh, small alphabets (the full-width workhorse)
-            switch (K) {
-                case 8: return strip_kernel<L, A, 8, true, false, 0>;
-                case 16: return strip_kernel<L, A, 16, true, false, 0>;
-                case 32: return strip_kernel<L, A, 32, true, false, 0>;
-                default: break;
-            }
+#if ANYSEQ_INST_AFFINE
+    if (mask && form == 0) {          // coupled cells: Gotoh, small alphabets (the full-width workhorse)
+        switch (K) {
+            case 8: return strip_kernel<L, A, 8, true, false, 0>;
+            case 16: return strip_kernel<L, A, 16, true, false, 0>;
+            case 32: return strip_kernel<L, A, 32, true, false, 0>;
+            default: break;
         }
     }
+#else
+    (void)form;
+#endif
     if (mask) {
         switch (K) {
             case 4: return strip_kernel<L, A, 4, true>;

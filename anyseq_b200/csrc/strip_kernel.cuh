@@ -49,8 +49,13 @@ namespace anyseq {
 // three warps per scheduler can be fed (Gotoh, strips >> warps: 3.71 vs 3.52 TCUPS on the 4.6 Mbp pair), the decoupled
 // form everywhere else (linear gaps, single-band launches, small problems, multi-GPU slices).
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 4;                       // batch kernels, end-cell tracking strip kernels
 constexpr int kThreads = kWarpsPerBlock * kWarp;
+// The strip kernels run ONE CTA per SM with 4, 8 or 12 warps (1 - 3 per scheduler; warp w issues on scheduler w % 4):
+// the warps that share a scheduler take ADJACENT strips.  When the right one of them has to wait for its left
+// neighbour, the neighbour is the warp that inherits its issue slots, so a pair (or triple) of strips behaves like one
+// wide strip with two (three) instruction streams instead of two unrelated streams that disturb each other's pace.
+constexpr int kMaxStripWarps = 12;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxCodes = 32;      // MASK kernels: alphabet codes incl. code 0 = "matches nothing"
 
@@ -869,11 +874,11 @@ constexpr int strip_min_blocks()
 }
 
 template <bool LOCAL, bool AFFINE, int K, bool MASK, bool TRACK = false, int FORM = 1>
-__global__ void __launch_bounds__(kThreads, TRACK ? (K >= 32 ? 4 : (K >= 16 ? 5 : 6)) : strip_min_blocks<K, MASK>())
+__global__ void __launch_bounds__(TRACK ? kThreads : kMaxStripWarps * kWarp, TRACK ? (K >= 32 ? 4 : (K >= 16 ? 5 : 6)) : 1)
 strip_kernel(const KernelArgs a)
 {
     constexpr int R = TRACK ? 1 : StripRows<K, MASK>::value;
-    __shared__ WarpSmem s_warp[kWarpsPerBlock];
+    __shared__ WarpSmem s_warp[TRACK ? kWarpsPerBlock : kMaxStripWarps];
     __shared__ uint8_t s_lut[MASK ? 512 : 4];
     extern __shared__ unsigned s_dyn[];          // MASK: [warps][ncodes][32][W] spread column masks
 
@@ -881,7 +886,7 @@ strip_kernel(const KernelArgs a)
     const int lane = threadIdx.x & 31;
     constexpr int SW = kWarp * K;
     if constexpr (MASK) {
-        for (int x = threadIdx.x; x < 256; x += kThreads) {
+        for (int x = threadIdx.x; x < 256; x += blockDim.x) {
             s_lut[x] = a.lut_q[x];
             s_lut[256 + x] = a.lut_s[x];
         }
@@ -897,7 +902,9 @@ strip_kernel(const KernelArgs a)
     // the static assignment): every item only waits on lower-numbered items, which
     // were claimed earlier by warps that are resident, so no wait can be circular.
     int jcur = 0;
-    long long item = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    // first round: static; the warps of one scheduler (w, w + 4, w + 8) get neighbouring items
+    const int wpb = blockDim.x >> 5, per_sched = wpb >> 2;
+    long long item = (long long)blockIdx.x * wpb + (warp & 3) * per_sched + (warp >> 2);
     for (; item < a.total_items;) {
         const int band = (int)(item / a.strips_total);
         const int rem = (int)(item % a.strips_total);

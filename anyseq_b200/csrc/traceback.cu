@@ -293,7 +293,7 @@ int Engine::align_host(const anyseq_scoring& sc, const char* q, int m, const cha
     rc = analyse_alphabet(d_q, m, d_s, n);
     if (rc) return rc;
     launches += 3;
-    const int Ktop = pick_K(n);
+    const int Ktop = pick_K_levels(n);
     std::vector<Job> jobs;
     std::vector<HbPart> parts;
 
