@@ -178,13 +178,16 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool trac
     return affine ? get_strip_kernel_01(K, mask, form) : get_strip_kernel_00(K, mask, form);
 }
 
-// Cell form of a launch (strip_kernel.cuh): coupled cells need three warps per scheduler to fill the issue slots, which
-// only a launch with many more strips than warps can feed; everything else runs the decoupled cells, whose lone warps
-// are 1.5x faster (measured on a B200: 670 vs 1008 cycles per two-row step of a K = 32 strip).
-static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long long strips_total, int sm_count)
+// Cell form of a launch (strip_kernel.cuh).  With the warps of a scheduler on adjacent strips the decoupled cells are
+// at least as fast as the coupled ones everywhere they were measured on a B200 (4.6 Mbp pair, three warps per scheduler:
+// 3883 vs 3853 GCUPS; 575 k-column slice: 3188 vs 2846; 1 Mbp x 1 Mbp: 3157 vs 2500; lone warps: 670 vs 1008 cycles per
+// step) -- except for the LOCAL Gotoh cell, whose decoupled form needs one more instruction per cell: wide local Gotoh
+// launches (enough strips for three warps per scheduler over several rounds) keep the coupled cells.
+static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long long strips_total, int sm_count, bool local)
 {
-    if (tune.cell_form == 0 || tune.cell_form == 1) return (affine && mask && K >= 8) ? tune.cell_form : 1;
-    return (affine && mask && K >= 8 && strips_total >= 10LL * sm_count) ? 0 : 1;
+    const bool has_coupled = affine && mask && K >= 8;
+    if (tune.cell_form == 0 || tune.cell_form == 1) return has_coupled ? tune.cell_form : 1;
+    return (has_coupled && local && strips_total >= 24LL * sm_count) ? 0 : 1;
 }
 
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)
@@ -204,10 +207,11 @@ static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max
     int nb = occupancy_max;
     if (rows_per_step(K, mask, track) >= 2) {
         const long long per_round = 4LL * sm_count;              // warps of one CTA per SM
-        // enough CTAs for every strip to have its own warp (single-band launches), at most what the cell form can use:
-        // the decoupled cells saturate the ALU pipe with two warps per scheduler, the coupled ones want three
+        // enough warps for every strip to have its own (single-band launches), at most three per scheduler (measured
+        // on the 4.6 Mbp pair, decoupled cells: 3736 GCUPS with two, 3883 with three; linear gaps 5376 / 5687)
         const int want = (int)std::max<long long>(1, (nstrips + per_round - 1) / per_round);
-        nb = std::min(nb, std::min(form == 0 ? 3 : 2, want));
+        nb = std::min(nb, std::min(3, want));
+        (void)form;
     }
     return nb;
 }
@@ -340,7 +344,7 @@ void Engine::destroy()
 
 int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
-    const int form = pick_form(tune, affine, use_mask_, K, nstrips, sm_count);
+    const int form = pick_form(tune, affine, use_mask_, K, nstrips, sm_count, local);
     KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) return 0;
     const bool track = track_ && local;
@@ -412,26 +416,17 @@ int Engine::pick_K_levels(int n_total) const
 
 int Engine::pick_K(int n, bool chained) const
 {
+    (void)chained;
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
         tune.cols_per_lane == 32)
         return tune.cols_per_lane;
-    // At most one warp works on a strip at a time, so the strips must at least
-    // cover the warps the kernel variant runs with; beyond that, wider strips have
-    // less per-step overhead.  Thresholds from B200 measurements (profiles/), semiglobal
-    // Gotoh, GCUPS: n = 100 k: 1116 at K=8 (four-row tiles) vs 640 at K=16; 400 k: 2345 vs 1887;
-    // 575 k: 2859 vs 2711; 800 k: 2904 vs 2807; 1.15 M: 2954 vs 3196 at K=16 (3100 at K=32);
-    // 2.3 M: 3600 at K=32.
-    if (use_mask_) {
-        if (n >= 1800000) return 32;
-        // A slice of a multi-GPU wavefront also sits in a chain over the ranks, whose fill time grows with
-        // strips x rows of lag: K = 8 (twice the strips, 224 rows of lag) cost 1458 vs 1169 ms per alignment on
-        // 8 GPUs although the slice alone is 5 % faster -- chained slices keep the wider strips.
-        if (n >= (chained ? 280000 : 1000000)) return 16;
-        if (n >= (chained ? 70000 : 40000)) return 8;
-        return 4;
-    }
-    if (n >= 1500000) return 16;      // generic kernels keep subject bytes in registers: K <= 16
-    if (n >= 200000) return 8;
+    // The widest strips that still give every scheduler about two warps (which then sit on adjacent strips): wider
+    // strips have less per-step overhead and a shorter chain, but at most one warp works on a strip at a time.
+    // B200, semiglobal Gotoh, GCUPS: 575 k columns: 3188 at K = 16 (1124 strips) vs 2890 at K = 32, 3008 at K = 8;
+    // 1.15 M: 3513 at K = 32 (1124 strips) vs 3375 at K = 16; 1 M x 1 M: 3157 at K = 16 vs 2624 at K = 8.
+    const long long want = 7LL * sm_count;             // ~1040 strips on a B200
+    for (int K = use_mask_ ? 32 : 16; K > 4; K /= 2)   // generic kernels keep subject bytes in registers: K <= 16
+        if ((long long)n / (kWarp * K) >= want) return K;
     return 4;
 }
 
@@ -468,7 +463,7 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     }
     if (strips_total > 0x7fffffff) { set_last_error("too many strips in one launch"); return ANYSEQ_ERR_UNSUPPORTED; }
 
-    const int form = pick_form(tune, affine, use_mask_, K, strips_total, sm_count);
+    const int form = pick_form(tune, affine, use_mask_, K, strips_total, sm_count, local);
     KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
     const bool track = track_ && local;

@@ -893,21 +893,24 @@ def test_sharded_traceback_equals_single_gpu(oracle):
             for sch in (A.linear_scoring_scheme(2, -1, -1), A.affine_scoring_scheme(2, -1, -2, -1)):
                 for mode in MODES:
                     bar = threading.Barrier(world)
-                    slot = {}
-                    pieces = [None] * world
+                    gpu = threading.Lock()      # the emulated ranks share ONE GPU: their persistent (cooperative) kernels
+                    slot = {}                   # must never run at the same time, so a rank holds this token while it
+                    pieces = [None] * world     # computes and hands it over inside the exchange callback
                     errors = []
 
                     def make_cb(rank):
                         def cb(user, ptr, nbytes, src):
                             try:
+                                gpu.release()               # the engine has synchronised its stream before calling back
                                 if rank == src:
                                     slot["ptr"] = ptr
-                                bar.wait(timeout=60)
+                                bar.wait(timeout=120)
                                 if rank != src:
                                     dst = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
                                     dst.copy_(torch.as_tensor(_DevView(slot["ptr"], nbytes), device="cuda"))
                                     torch.cuda.synchronize()
-                                bar.wait(timeout=60)
+                                bar.wait(timeout=120)
+                                gpu.acquire()
                                 return 0
                             except Exception as e:          # pragma: no cover
                                 errors.append(e)
@@ -918,7 +921,8 @@ def test_sharded_traceback_equals_single_gpu(oracle):
                         try:
                             st = ShardedTraceback(als[rank], rank, world, dist=None)
                             st._cb = make_cb(rank)
-                            pieces[rank] = st.align(mode, q, s, sch)
+                            with gpu:
+                                pieces[rank] = st.align(mode, q, s, sch)
                         except Exception as e:
                             errors.append(e)
                             bar.abort()
