@@ -971,3 +971,32 @@ def test_full_size_c3_affine_traceback_against_cpu(aligner):
     assert _sha(r.aligned_query, r.aligned_subject) == gold["sha"]
     assert hashlib.sha256(np.asarray(aligner.last_splits(), dtype=np.int32).tobytes()).hexdigest()[:16] == gold["splits_sha"]
     assert hashlib.sha256(np.asarray(aligner.last_split_types(), dtype=np.int32).tobytes()).hexdigest()[:16] == gold["types_sha"]
+
+
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("K", [8, 16, 32])
+def test_both_cell_forms_vs_oracle(aligner, oracle, form, K):
+    """the coupled (round 1) and the decoupled cell form of the Gotoh kernels (strip_kernel.cuh: FORM) must both
+    reproduce the restated reference on every scheme: the engine picks a form per launch, this forces each one,
+    with several bands, 1 - 3 warps per scheduler and ragged widths"""
+    import anyseq_b200 as A
+    rng = np.random.default_rng(555 + K)
+    schemes = [A.affine_scoring_scheme(2, -1, -2, -1), A.affine_scoring_scheme(5, -4, -10, -1), A.affine_scoring_scheme(1, -1, -1, 0)]
+    shapes = [(300, 1025), (2100, 32 * K * 3 + 17), (1500, 32 * K * 7), (4099, 2000)]
+    aligner.set_option("cell_form", form)
+    try:
+        for bps, band in ((1, 0), (2, 512), (3, 0)):
+            aligner.tune(cols_per_lane=K, band_rows=band, blocks_per_sm=bps, watchdog_ms=10000)
+            for (m, n) in shapes:
+                q = _rand(rng, m)
+                s = _related(rng, q, n, sub=0.12)
+                for mode in MODES:
+                    for sch in schemes:
+                        r = aligner.score(mode, q, s, sch)
+                        ref = oracle.score_affine(mode, q, s, sch.same, sch.diff, sch.gap_init, sch.gap_extend)
+                        assert r.score == ref[0], (form, K, bps, band, m, n, mode, sch)
+                        if mode != "local":
+                            assert (r.end_i, r.end_j) == ref[1:], (form, K, bps, band, m, n, mode, sch)
+    finally:
+        aligner.set_option("cell_form", -1)
+        aligner.tune(0, 0, 0, 10000)
