@@ -71,7 +71,7 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
         t.watchdog_ms = value;
     }
     else if (n == "band_slack" && value >= 1) t.band_slack = value;
-    else if (n == "cell_form" && value >= -1 && value <= 1) t.cell_form = value;
+    else if (n == "cell_form" && value >= -1 && value <= 2) t.cell_form = value;
     else if (n == "force_generic") t.force_generic = value != 0;
     else if (n == "force_affine") t.force_affine = value != 0;
     else if (n == "local_end_cell") t.local_end_cell = value != 0;

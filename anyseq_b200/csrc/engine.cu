@@ -187,6 +187,7 @@ static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long lon
 {
     const bool has_coupled = affine && mask && K >= 8;
     if (tune.cell_form == 0 || tune.cell_form == 1) return has_coupled ? tune.cell_form : 1;
+    if (tune.cell_form == 2) return (has_coupled && K >= 16) ? 2 : 1;
     return (has_coupled && local && strips_total >= 24LL * sm_count) ? 0 : 1;
 }
 
@@ -437,7 +438,7 @@ int Engine::pick_K(int n, bool chained) const
 // delays accumulate (measured: ~290 rows in the middle of a band for lone warps, against 105-136 at the start) --
 // costs nothing.  Otherwise a band must be high enough for the whole window to overlap with slack for that drift:
 // band_h = band_slack * lag * window; the price of higher bands is only the last, partially filled round of items.
-int Engine::plan_bands(int max_h, long long strips_total, int resident, int K) const
+int Engine::plan_bands(int max_h, long long strips_total, int resident, int K, bool chained) const
 {
     if (tune.band_rows > 0) {
         const int bh = std::max(32, (tune.band_rows + 31) / 32 * 32);
@@ -445,7 +446,10 @@ int Engine::plan_bands(int max_h, long long strips_total, int resident, int K) c
     }
     if (strips_total <= resident) return 1;
     const long long lag = 32LL * rows_per_step(K, use_mask_, track_) + 96;
-    const long long target = std::max<long long>(lag * resident * tune.band_slack, 4096);
+    // a rank of a multi-GPU wavefront: the next rank can only start when this rank's LAST strip has begun its first
+    // band, i.e. about one band time after the launch -- lower bands there (slack 1 costs 1 % on one GPU: 3671 vs 3710)
+    const long long slack = chained ? 1 : tune.band_slack;
+    const long long target = std::max<long long>(lag * resident * slack, 4096);
     return (int)std::max<long long>(1, (max_h + target - 1) / target);
 }
 
@@ -476,7 +480,9 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     const int resident = nb * kWarpsPerBlock * sm_count;
 
     // bands: the same number for every job of the launch (items are ordered band, job, strip)
-    const int nbands = plan_bands(max_h, strips_total, resident, K);
+    bool chained = false;
+    for (const Job& j : jobs) chained = chained || j.in != nullptr || j.out != nullptr;
+    const int nbands = plan_bands(max_h, strips_total, resident, K, chained);
     for (Job& j : jobs) {
         const int bh = (j.h + nbands - 1) / nbands;
         j.band_h = std::max(32, (bh + 31) / 32 * 32);

@@ -32,6 +32,13 @@ StripKernelFn ANYSEQ_INST_NAME(int K, bool mask, int form)
     }
 #else
 #if ANYSEQ_INST_AFFINE
+    if (mask && form == 2) {          // mixed cells (even rows coupled, odd rows decoupled): two-row tiles only
+        switch (K) {
+            case 16: return strip_kernel<L, A, 16, true, false, 2>;
+            case 32: return strip_kernel<L, A, 32, true, false, 2>;
+            default: break;
+        }
+    }
     if (mask && form == 0) {          // coupled cells: Gotoh, small alphabets (the full-width workhorse)
         switch (K) {
             case 8: return strip_kernel<L, A, 8, true, false, 0>;

@@ -242,7 +242,19 @@ struct StepConst {
     int one, ge, go, diff_o, same_o;
     int nvalid, outc;   // PARTIAL only
     unsigned capmask;   // PARTIAL only: bit outc
+    int diff_c, same_c; // FORM 2: sigma - go for the coupled rows of a mixed tile
 };
+
+template <int BASE, int W>
+__device__ __forceinline__ int diag_mask_bit_c(const unsigned (&tm)[W], int r, int d, int one, int diff_o, int same_o)
+{
+    switch (r) {
+        case 0: return diag_plus_sigma_mask<(BASE + 0) % 32>(tm[(BASE + 0) / 32 < W ? (BASE + 0) / 32 : 0], d, one, diff_o, same_o);
+        case 1: return diag_plus_sigma_mask<(BASE + 1) % 32>(tm[(BASE + 1) / 32 < W ? (BASE + 1) / 32 : 0], d, one, diff_o, same_o);
+        case 2: return diag_plus_sigma_mask<(BASE + 2) % 32>(tm[(BASE + 2) / 32 < W ? (BASE + 2) / 32 : 0], d, one, diff_o, same_o);
+        default: return diag_plus_sigma_mask<(BASE + 3) % 32>(tm[(BASE + 3) / 32 < W ? (BASE + 3) / 32 : 0], d, one, diff_o, same_o);
+    }
+}
 
 template <int BASE, int W>
 __device__ __forceinline__ int diag_mask_bit(const unsigned (&tm)[W], int r, int d, const StepConst& k)
@@ -371,13 +383,36 @@ struct CellR {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int dd = s.dd[r];
+            // FORM 2 ("mixed", Gotoh two-row tiles): even rows coupled (3 ALU-pipe ops per cell), odd rows decoupled (4) --
+            // the decoupled kernel is ALU-pipe bound (94 % busy, ncu), the coupled one latency bound; half and half has
+            // 12 % less ALU work than the one and a short chain in every other row unlike the other
+            const bool coupled_row = (FORM == 0) || (FORM == 2 && (r & 1) == 0);
             if constexpr (C + 1 < K) {
                 // diagonal term of cell (r, C+1): H(r-1, C) = the cell above this one
-                if constexpr (MASK) s.dd[r] = diag_mask_bit<(C + 1) * R>(s.tm, r, above_x, k);
-                else s.dd[r] = diag_plus_sigma(s.qc[r], sc[C + 1], above_x, k.one, k.diff_o, k.same_o);
+                if constexpr (MASK) {
+                    if (FORM == 2 && coupled_row) s.dd[r] = diag_mask_bit_c<(C + 1) * R>(s.tm, r, above_x, k.one, k.diff_c, k.same_c);
+                    else s.dd[r] = diag_mask_bit<(C + 1) * R>(s.tm, r, above_x, k);
+                } else {
+                    s.dd[r] = diag_plus_sigma(s.qc[r], sc[C + 1], above_x, k.one, k.diff_o, k.same_o);
+                }
             }
             int h, x;
-            if constexpr (FORM == 1 && AFFINE) {
+            if (FORM == 2 && AFFINE && coupled_row) {
+                s.e[r] = __viaddmax_s32(s.e[r], k.ge, s.x[r]);
+                const int f = __viaddmax_s32(above_f, k.ge, above_x);
+                h = LOCAL ? __vimax3_s32_relu(dd, s.e[r], f) : __vimax3_s32(dd, s.e[r], f);
+                x = imad_add(h, k.one, k.go);
+                above_f = f;
+                hrow[r] = x;                    // the local maximum is tracked on X in this form
+                s.x[r] = x;
+                above_x = x;
+                if constexpr (PARTIAL != 0) {
+                    capture_if_bit<C>(k.capmask, s.xs[r], x, k.one);
+                    capture_if_bit<C>(k.capmask, s.es[r], s.e[r], k.one);
+                }
+                continue;
+            }
+            if constexpr ((FORM == 1 || FORM == 2) && AFFINE) {
                 // decoupled form (see Cell): s.x[r] carries M of the cell to the left, hrow holds X (= H + go)
                 const int f = __viaddmax_s32(above_f, k.ge, above_x);
                 int mp;
@@ -487,8 +522,11 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     k.ge = a.sp.gap_extend;
     k.go = go;
     // coupled form: dd = H_diag + sigma = X_diag + (sigma - go); decoupled form: dd = X_diag + sigma
-    k.diff_o = FORM == 1 ? a.sp.diff : a.sp.diff - go;
-    k.same_o = FORM == 1 ? a.sp.same : a.sp.same - go;
+    k.diff_o = FORM >= 1 ? a.sp.diff : a.sp.diff - go;
+    k.same_o = FORM >= 1 ? a.sp.same : a.sp.same - go;
+    k.diff_c = a.sp.diff - go;
+    k.same_c = a.sp.same - go;
+    static_assert(FORM != 2 || (MASK && AFFINE && R == 2), "mixed cells: Gotoh two-row MASK tiles");
     int* const status = a.status;
     const unsigned long long timeout_ns = a.timeout_ns;
 
@@ -623,7 +661,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         dcarry = xl;
         st.xleft = xl;
         st.e = el;
-        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK, FORM>::run(X, F, sc, st, k);
+        Cell<LOCAL, AFFINE, K, PARTIAL, MASK, R, RO, 0, TRACK, (FORM == 2 ? 1 : FORM)>::run(X, F, sc, st, k);
         hro = st.xleft;
         ero = st.e;
         if constexpr (PARTIAL != 0) {
@@ -671,7 +709,8 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 s2.qc[r] = 0;
                 const int dg = (r == 0) ? dcarry : xl[r - 1];      // H(row-1, first column - 1)
                 if constexpr (MASK) {
-                    s2.dd[r] = diag_mask_bit<0>(s2.tm, r, dg, k);
+                    if (FORM == 2 && (r & 1) == 0) s2.dd[r] = diag_mask_bit_c<0>(s2.tm, r, dg, k.one, k.diff_c, k.same_c);
+                    else s2.dd[r] = diag_mask_bit<0>(s2.tm, r, dg, k);
                 } else {
                     s2.qc[r] = sm.q[(R * g + r) & QM];
                     s2.dd[r] = diag_plus_sigma(s2.qc[r], sc[0], dg, k.one, k.diff_o, k.same_o);
@@ -828,8 +867,8 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         if constexpr (!PARTIAL) best = max(best, st.hprev);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
-        if constexpr (FORM == 1 && AFFINE) {
-            if (best > kScoreMin) best -= go;             // the decoupled Gotoh cells track X = H + go
+        if constexpr (FORM >= 1 && AFFINE) {
+            if (best > kScoreMin) best -= go;             // the decoupled (and mixed) Gotoh cells track X = H + go
         }
         if (lane == 0) atomicMax(J.best, best);
     }

@@ -18,12 +18,31 @@ from .api import Aligner, AlignmentResult, ScoringScheme
 from .capi import Result, StripPartial, make_scoring
 
 
-def column_slices(n: int, world: int, align: int = 1024):
-    """equal slices of [0, n), boundaries rounded to `align` columns"""
-    cuts = [0]
-    for r in range(1, world):
-        c = (n * r // world) // align * align
-        cuts.append(max(c, cuts[-1]))
+def _strip_cols(width: int, sm_count: int = 148) -> int:
+    """strip width the engine picks for a slice of `width` columns (engine.cu: pick_K, small alphabets)"""
+    for k in (32, 16, 8):
+        if width // (32 * k) >= 7 * sm_count:
+            return 32 * k
+    return 128
+
+
+def column_slices(n: int, world: int, align: int = 1024, rows: int = 0, strip_cols: int = 0, lag_rows: int = 100):
+    """slices of [0, n), boundaries rounded to `align` columns.  rows == 0: equal slices.  rows > 0 (one long pair as
+    a wavefront over the ranks): rank r can only start when the wavefront has crossed the slices before it, so equal
+    slices leave rank 0 idle at the end and make the last rank the critical path; the slices shrink geometrically
+    instead so that ALL ranks finish together.  With f = (strips of a slice) * lag_rows / rows the fill of a slice
+    relative to its work, a slice is 1 / (1 + f) of its left neighbour; the makespan drops from C + world * fill to
+    about C + (world + 1) / 2 * fill (4.6 Mbp on 8 GPUs: 7 % less)."""
+    weights = [1.0] * world
+    if rows > 0 and world > 1:
+        f = (n / world / (strip_cols or _strip_cols(n // world))) * lag_rows / float(rows)
+        weights = [(1.0 / (1.0 + f)) ** r for r in range(world)]
+    total = sum(weights)
+    cuts, acc = [0], 0.0
+    for r in range(world - 1):
+        acc += weights[r]
+        c = int(n * acc / total) // align * align
+        cuts.append(min(max(c, cuts[-1]), n))
     cuts.append(n)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 

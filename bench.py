@@ -386,7 +386,7 @@ def main():
     al = A.Aligner(local_rank)
     info = al.device_info()
 
-    slices = column_slices(n, world)
+    slices = column_slices(n, world, rows=m)      # shrinking slices: all ranks of the wavefront finish together
     c0, c1 = slices[rank]
     h_q = torch.from_numpy(q).pin_memory()
     h_s = torch.from_numpy(np.ascontiguousarray(s[c0:c1])).pin_memory()
@@ -535,9 +535,9 @@ def main():
         "bound": "int_alu",
         "achieved": achieved_ops / 1e12, "peak": peak_alu / 1e12, "unit": "Tlaneop/s (int32, per GPU)",
         "frac": achieved_ops / peak_alu,
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE strip-kernel launch at this workload
-        # (ncu, profiles/r01_strip_kernel_fullsize_metrics.csv): 232.7 MB + 325.1 MB; only valid for N = 1
-        "traffic": 557_788_672 if (world == 1 and args.scale == 1.0) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE strip-kernel launch at this workload (ncu --set full,
+        # profiles/r02_strip_kernel_fullsize_ncu_full.txt): 134.2 MB + 171.3 MB; only valid for N = 1
+        "traffic": 305_494_272 if (world == 1 and args.scale == 1.0) else None,
         "traffic_unit": "bytes of DRAM traffic per launch (algorithmic input: m + n = 9.24 MB; the border records live in L2)",
         "ops_per_cell": OPS_PER_CELL_AFFINE,
         "peak_source": "measured live: anyseq_measure_int_peak(kind=0), dependency-free VIADDMNMX/VIMNMX3 loop",
@@ -551,7 +551,7 @@ def main():
         "peak_gcups_mix7_measured": peak_mix7 / OPS_PER_CELL_AFFINE / 1e9,
         "peak_gcups_dual_pipe_mix": peak_cells_dual / 1e9,
         "frac_of_dual_pipe_mix": (value / world) / (peak_cells_dual / 1e9),
-        "hbm": {"achieved_gbs": (557_788_672 / (ms_per_step * 1e-3) / 1e9) if (world == 1 and args.scale == 1.0) else None,
+        "hbm": {"achieved_gbs": (305_494_272 / (ms_per_step * 1e-3) / 1e9) if (world == 1 and args.scale == 1.0) else None,
                 "peak_gbs": 6452.8, "note": "DRAM traffic of the strip kernel / step time; far below the HBM roofline by design"},
     }
 

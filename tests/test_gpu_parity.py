@@ -973,7 +973,7 @@ def test_full_size_c3_affine_traceback_against_cpu(aligner):
     assert hashlib.sha256(np.asarray(aligner.last_split_types(), dtype=np.int32).tobytes()).hexdigest()[:16] == gold["types_sha"]
 
 
-@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("form", [0, 1, 2])
 @pytest.mark.parametrize("K", [8, 16, 32])
 def test_both_cell_forms_vs_oracle(aligner, oracle, form, K):
     """the coupled (round 1) and the decoupled cell form of the Gotoh kernels (strip_kernel.cuh: FORM) must both

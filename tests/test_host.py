@@ -36,6 +36,13 @@ def test_column_slices():
             sl = column_slices(n, w)
             assert sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
     assert all(c0 % 1024 == 0 for c0, _ in column_slices(4_600_000, 8))
+    # wavefront slices: aligned, tiling, non-increasing widths, first about 18 % wider than the last on 8 ranks
+    sl = column_slices(4_600_000, 8, rows=4_641_652)
+    assert sl[0][0] == 0 and sl[-1][1] == 4_600_000 and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+    assert all(c0 % 1024 == 0 for c0, _ in sl)
+    w = [b - a for a, b in sl]
+    assert all(x >= y - 1024 for x, y in zip(w, w[1:])) and 1.05 < w[0] / w[-1] < 1.35
+    assert column_slices(1000, 1, rows=500) == [(0, 1000)]
 
 
 _WORKER = r'''
