@@ -178,17 +178,19 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool trac
     return affine ? get_strip_kernel_01(K, mask, form) : get_strip_kernel_00(K, mask, form);
 }
 
-// Cell form of a launch (strip_kernel.cuh).  With the warps of a scheduler on adjacent strips the decoupled cells are
-// at least as fast as the coupled ones everywhere they were measured on a B200 (4.6 Mbp pair, three warps per scheduler:
-// 3883 vs 3853 GCUPS; 575 k-column slice: 3188 vs 2846; 1 Mbp x 1 Mbp: 3157 vs 2500; lone warps: 670 vs 1008 cycles per
-// step) -- except for the LOCAL Gotoh cell, whose decoupled form needs one more instruction per cell: wide local Gotoh
-// launches (enough strips for three warps per scheduler over several rounds) keep the coupled cells.
+// Cell form of a launch (strip_kernel.cuh: 0 = coupled, 1 = decoupled, 2 = mixed).  Measured on a B200 with the warps of
+// a scheduler on adjacent strips, semiglobal Gotoh, GCUPS, coupled / decoupled / mixed: 4.6 Mbp pair, three warps per
+// scheduler: 3853 / 3885 / 3974 (local: 3315 / 3038 / 3505); 575 k-column slice, two per scheduler: 2846 / 3195 / 3159;
+// lone warps (K = 32 slice): 2214 / 2885 / 2753; 1 Mbp x 1 Mbp: 2500 / 3157 / 2654.  So: the mixed cells where a launch
+// has enough strips for three warps per scheduler over several rounds (ALU-pipe work 253 instead of 285 instructions
+// per 64 cells, and two other warps to hide the coupled rows' chain), the decoupled cells everywhere else.
 static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long long strips_total, int sm_count, bool local)
 {
+    (void)local;
     const bool has_coupled = affine && mask && K >= 8;
     if (tune.cell_form == 0 || tune.cell_form == 1) return has_coupled ? tune.cell_form : 1;
     if (tune.cell_form == 2) return (has_coupled && K >= 16) ? 2 : 1;
-    return (has_coupled && local && strips_total >= 24LL * sm_count) ? 0 : 1;
+    return (has_coupled && K >= 16 && strips_total >= 24LL * sm_count) ? 2 : 1;
 }
 
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)

@@ -43,8 +43,8 @@ def test_sass_is_sm100a_with_dpx():
     from anyseq_b200 import capi
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    # the headline kernel: strip_kernel<LOCAL=0, AFFINE=1, K=32, MASK=1, TRACK=0, FORM=0> (six template arguments)
-    hot = "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0ELi0EEEvNS_10KernelArgsE"
+    # the headline kernel: strip_kernel<LOCAL=0, AFFINE=1, K=32, MASK=1, TRACK=0, FORM=2> (six template arguments)
+    hot = "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0ELi2EEEvNS_10KernelArgsE"
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", hot, capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "Function : " + hot in sass, "hot kernel not found in the library (mangled name changed?)"
     n_dpx = sass.count("VIADDMNMX") + sass.count("VIMNMX3")
