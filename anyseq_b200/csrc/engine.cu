@@ -510,10 +510,18 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
 #endif
 
-    // few items: spread them over the SMs with 4-warp CTAs (one warp per scheduler) before doubling up
-    const int wpb_used = (total <= (long long)kWarpsPerBlock * sm_count) ? kWarpsPerBlock : wpb;
-    long long want_blocks = (total + wpb_used - 1) / wpb_used;
-    int grid = (int)std::min<long long>((long long)ctas_per_sm * sm_count, std::max<long long>(want_blocks, 1));
+    // launch shape: ONE CTA per SM for the ordinary kernels (nb CTAs of 4 warps for the tracking kernels); with few
+    // items, just enough warps per CTA that every item of the first round has one, spread evenly over all SMs
+    int wpb_used = wpb;
+    int grid;
+    if (track) {
+        grid = (int)std::min<long long>((long long)ctas_per_sm * sm_count, std::max<long long>((total + wpb - 1) / wpb, 1));
+    } else {
+        grid = (int)std::min<long long>(sm_count, std::max<long long>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 1));
+        const long long per_cta = (total + grid - 1) / grid;                   // items of the fullest CTA
+        wpb_used = (int)std::min<long long>(wpb, (per_cta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock);
+    }
+    const long long first_items = std::min<long long>(total, (long long)grid * wpb_used);
 
     {
         int maxlen = 1;
@@ -534,12 +542,13 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ka.status = misc_.as<int>() + kMiscStatus;
     ka.next_item = reinterpret_cast<unsigned long long*>(misc_.as<int>() + kMiscCounter);
     {
-        const unsigned long long first = (unsigned long long)grid * wpb_used;
+        const unsigned long long first = (unsigned long long)first_items;
         ANYSEQ_CUDA_CHECK(cudaMemcpyAsync(ka.next_item, &first, sizeof(first), cudaMemcpyHostToDevice, stream_));
     }
     ka.timeout_ns = (unsigned long long)tune.watchdog_ms * 1000000ull;
     ka.strips_total = (int)strips_total;
     ka.strip2job = d_strip2job;
+    ka.first_items = first_items;
     void* args[] = {&ka};
     ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(wpb_used * kWarp), args,
                                                   mask_smem_bytes(use_mask_, track, ncodes_, K, wpb_used), stream_));

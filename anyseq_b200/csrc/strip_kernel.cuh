@@ -76,6 +76,7 @@ struct KernelArgs {
     // Job::item_begin is the launch-wide index of its first strip.
     int strips_total;
     const int* strip2job;
+    long long first_items;          // items of the static first round (<= gridDim.x * warps per CTA), spread evenly over the CTAs
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -941,9 +942,25 @@ strip_kernel(const KernelArgs a)
     // the static assignment): every item only waits on lower-numbered items, which
     // were claimed earlier by warps that are resident, so no wait can be circular.
     int jcur = 0;
-    // first round: static; the warps of one scheduler (w, w + 4, w + 8) get neighbouring items
-    const int wpb = blockDim.x >> 5, per_sched = wpb >> 2;
-    long long item = (long long)blockIdx.x * wpb + (warp & 3) * per_sched + (warp >> 2);
+    // First round: static.  CTA b gets items [b F / G, (b + 1) F / G) (F = a.first_items, G = gridDim.x: every SM gets its
+    // share even when there are fewer items than warps); inside the CTA the items go to the schedulers in runs, so the warps
+    // of one scheduler (w, w + 4, w + 8) work on neighbouring strips.  A warp without an item claims one dynamically.
+    long long item;
+    {
+        const long long lo = (long long)blockIdx.x * a.first_items / gridDim.x;
+        const int cnt = (int)((long long)(blockIdx.x + 1) * a.first_items / gridDim.x - lo);
+        const int sch = warp & 3, slot = warp >> 2;
+        const int base = cnt >> 2, rem = cnt & 3;
+        const int mine = base + (sch < rem ? 1 : 0);           // items of this scheduler
+        const int off = sch * base + min(sch, rem);
+        if (slot < mine) {
+            item = lo + off + slot;
+        } else {
+            unsigned long long nxt = 0;
+            if (lane == 0) nxt = atomicAdd(a.next_item, 1ull);
+            item = (long long)__shfl_sync(kFull, nxt, 0);
+        }
+    }
     for (; item < a.total_items;) {
         const int band = (int)(item / a.strips_total);
         const int rem = (int)(item % a.strips_total);

@@ -304,7 +304,8 @@ int Engine::align_host_affine(const anyseq_scoring& sc, const char* q, int m, co
     rc = analyse_alphabet(d_q, m, d_s, n);
     if (rc) return rc;
     launches += 3;
-    const int Ktop = pick_K_levels(n);
+    // a rank of a sharded traceback relaxes 1 / world of the columns of every level: strips for ITS schedulers
+    const int Ktop = pick_K_levels(n / sworld);
     std::vector<Job> jobs;
     std::vector<HbPartA> parts;
 

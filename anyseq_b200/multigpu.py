@@ -336,6 +336,28 @@ class ShardedTraceback:
     def gather(self, m: int, n: int, piece):
         """all-gather of the pieces -> (aligned_query, aligned_subject, splits) identical on every rank"""
         lo, hi, q, s, splits, _ = piece
+        if self.world > 1 and self.dist.get_backend() == "nccl":
+            # the strings over NVLink: every rank fills its columns of a zeroed device buffer, one all-reduce (the
+            # ranges are disjoint); the ranges and split rows (small) as objects
+            torch = self._torch
+            total = m + n
+            buf = torch.zeros(2 * total, dtype=torch.uint8, device="cuda")
+            if hi > lo:
+                buf[lo:hi] = torch.frombuffer(bytearray(q), dtype=torch.uint8).cuda()
+                buf[total + lo: total + hi] = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM)
+            meta = [None] * self.world
+            self.dist.all_gather_object(meta, (lo, hi, splits))
+            pos = 0
+            for (l, h, _) in meta:                      # the ranges must tile [0, m + n)
+                if h > l:
+                    if l != pos:
+                        raise ValueError(f"traceback regions do not tile the output: expected a piece starting at {pos}, got [{l}, {h})")
+                    pos = h
+            if pos != total:
+                raise ValueError(f"traceback regions end at {pos}, not at {total}")
+            host = buf.cpu().numpy()
+            return host[:total].tobytes(), host[total:].tobytes(), merge_splits([x[2] for x in meta])
         pieces = [(lo, hi, q, s, splits)]
         if self.world > 1:
             pieces = [None] * self.world

@@ -82,6 +82,8 @@ if world & (world - 1) == 0:
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         piece = st.align(mode, tq, ts, tsch)
+        dist.barrier()
+        t_align = time.perf_counter() - t0
         aq, as_, splits = st.gather(tb_n, tb_n, piece)
         dist.barrier()
         t_multi = time.perf_counter() - t0
@@ -92,7 +94,7 @@ if world & (world - 1) == 0:
             t_one = time.perf_counter() - t0
             same = (aq, as_) == (one.aligned_query, one.aligned_subject) and splits == al.last_splits()
             g = gold.get("c3affine_local") if (name == "affine" and mode == "local" and tb_n == 1000000) else None
-            print(f"sharded traceback {name} {mode} {tb_n} x {tb_n}: {world} GPUs {t_multi*1e3:.1f} ms, 1 GPU {t_one*1e3:.1f} ms "
+            print(f"sharded traceback {name} {mode} {tb_n} x {tb_n}: {world} GPUs {t_multi*1e3:.1f} ms (align {t_align*1e3:.1f} + gather), 1 GPU {t_one*1e3:.1f} ms "
                   f"(x{t_one/t_multi:.2f}), identical={same}, sha={sha}" + (f", frozen CPU sha equal={sha == g['sha']}" if g else ""), flush=True)
             assert same
             if g:
