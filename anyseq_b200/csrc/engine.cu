@@ -210,9 +210,13 @@ static int default_blocks_per_sm(int K, bool mask, bool track, int occupancy_max
     int nb = occupancy_max;
     if (rows_per_step(K, mask, track) >= 2) {
         const long long per_round = 4LL * sm_count;              // warps of one CTA per SM
-        // enough warps for every strip to have its own (single-band launches), at most three per scheduler (measured
-        // on the 4.6 Mbp pair, decoupled cells: 3736 GCUPS with two, 3883 with three; linear gaps 5376 / 5687)
-        const int want = (int)std::max<long long>(1, (nstrips + per_round - 1) / per_round);
+        // Enough warps for every strip to have its own (single-band launches), at most three per scheduler (measured
+        // on the 4.6 Mbp pair, decoupled cells: 3736 GCUPS with two, 3883 with three; linear gaps 5376 / 5687) -- but
+        // only if that loads the schedulers evenly: in a single-band chain the most loaded scheduler sets the pace of
+        // every strip to its right (1218 strips as 3+2+2+2 per SM: 2470 GCUPS; 1124 strips as 2+2+2+2: 3214).  A launch
+        // that would fill less than 80 % of the warps runs with one warp less and several bands.
+        int want = (int)std::max<long long>(1, (nstrips + per_round - 1) / per_round);
+        if (want > 1 && nstrips * 10 < (long long)want * per_round * 8) --want;
         nb = std::min(nb, std::min(3, want));
         (void)form;
     }

@@ -26,7 +26,8 @@ def _strip_cols(width: int, sm_count: int = 148) -> int:
     return 128
 
 
-def column_slices(n: int, world: int, align: int = 1024, rows: int = 0, strip_cols: int = 0, lag_rows: int = 100):
+def column_slices(n: int, world: int, align: int = 1024, rows: int = 0, strip_cols: int = 0, lag_rows: int = 100,
+                  sm_count: int = 148):
     """slices of [0, n), boundaries rounded to `align` columns.  rows == 0: equal slices.  rows > 0 (one long pair as
     a wavefront over the ranks): rank r can only start when the wavefront has crossed the slices before it, so equal
     slices leave rank 0 idle at the end and make the last rank the critical path; the slices shrink geometrically
@@ -34,14 +35,29 @@ def column_slices(n: int, world: int, align: int = 1024, rows: int = 0, strip_co
     relative to its work, a slice is 1 / (1 + f) of its left neighbour; the makespan drops from C + world * fill to
     about C + (world + 1) / 2 * fill (4.6 Mbp on 8 GPUs: 7 % less)."""
     weights = [1.0] * world
+    cap = float(n)
     if rows > 0 and world > 1:
-        f = (n / world / (strip_cols or _strip_cols(n // world))) * lag_rows / float(rows)
+        sc = strip_cols or _strip_cols(n // world)
+        f = (n / world / sc) * lag_rows / float(rows)
         weights = [(1.0 / (1.0 + f)) ** r for r in range(world)]
-    total = sum(weights)
+        # a slice must not need more strips than two warps per scheduler can take (the most loaded scheduler sets the
+        # pace of a single-band chain, engine.cu: default_blocks_per_sm), if the other ranks can absorb the rest
+        if sc * 8 * sm_count * world >= n:
+            cap = float(sc * 8 * sm_count)
+    widths = [n * w / sum(weights) for w in weights]
+    for _ in range(world):                       # clip to the cap, hand the excess to the unclipped slices
+        over = sum(max(0.0, w - cap) for w in widths)
+        free = [i for i, w in enumerate(widths) if w < cap]
+        if over <= 0 or not free:
+            break
+        fsum = sum(widths[i] for i in free)
+        widths = [min(w, cap) for w in widths]
+        for i in free:
+            widths[i] += over * widths[i] / fsum
     cuts, acc = [0], 0.0
     for r in range(world - 1):
-        acc += weights[r]
-        c = int(n * acc / total) // align * align
+        acc += widths[r]
+        c = int(acc) // align * align
         cuts.append(min(max(c, cuts[-1]), n))
     cuts.append(n)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
