@@ -16,12 +16,19 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 al = A.Aligner(local)
 sch = A.affine_scoring_scheme()
-wcols = int(os.environ.get("SLICE", "575488"))
 m = int(os.environ.get("ROWS", "4641652"))
-n = wcols * world
+if os.environ.get("SLICES") == "bench":        # the slices bench.py uses for the 4.6 Mbp pair
+    from anyseq_b200.multigpu import column_slices
+    widths = [b - a for a, b in column_slices(4_600_000, world, rows=m)]
+elif os.environ.get("SLICES"):
+    widths = [int(x) for x in os.environ["SLICES"].split(",")]
+else:
+    widths = [int(os.environ.get("SLICE", "575488"))] * world
+wcols = widths[rank]
+n = sum(widths)
 q = W.random_dna(m, 42)
 s = W.mutated_copy(q, n, 43) if n <= m else np.concatenate([W.mutated_copy(q, m, 43), W.random_dna(n - m, 44)])
-c0, c1 = rank * wcols, (rank + 1) * wcols
+c0 = sum(widths[:rank]); c1 = c0 + wcols
 d_q = torch.from_numpy(q).cuda()
 d_s = torch.from_numpy(np.ascontiguousarray(s[c0:c1])).cuda()
 res = {}
@@ -38,6 +45,6 @@ out = [None] * world
 dist.all_gather_object(out, (rank, res))
 if rank == 0:
     for r_, v in out:
-        print(f"rank {r_}: alone {v['alone']:.1f} ms, chained {v['chained']:.1f} ms", flush=True)
+        print(f"rank {r_}: {widths[r_]} columns, alone {v['alone']:.1f} ms, chained {v['chained']:.1f} ms", flush=True)
 wave.close()
 dist.destroy_process_group()
