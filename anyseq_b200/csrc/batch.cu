@@ -260,14 +260,19 @@ int Engine::launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool a
         const long long small = std::max<long long>({std::llabs(sc.same), std::llabs(sc.diff), std::llabs(go), std::llabs(sc.gap_extend)});
         if (b + hmax + 2 * small < 32000 && small < 2000) { packed = true; bias = (int)b; }
     }
-    BatchKernelFn fn = packed ? pick_batch_x2_kernel(sc.mode, affine, K) : pick_batch_kernel(sc.mode, affine, K, use_mask_);
+    // four pairs per warp (half-warps, batch_x2.cu: batch_x4_kernel) when the column sequences fit 16 lanes x 32 columns
+    const bool quad = packed && tune.batch_quad && ncols <= 512;
+    BatchKernelFn fn = quad ? pick_batch_x4_kernel(sc.mode, affine)
+                            : (packed ? pick_batch_x2_kernel(sc.mode, affine, K) : pick_batch_kernel(sc.mode, affine, K, use_mask_));
     if (!fn) { set_last_error("no batch kernel for this configuration"); return ANYSEQ_ERR_UNSUPPORTED; }
-    // packed: two mask sets, match bits spread to every other bit (2 K bits per lane and row)
-    const size_t dyn = use_mask_ ? sizeof(unsigned) * 32 * (size_t)ncodes_ * kWarpsPerBlock * (packed ? 2 * ((2 * K + 31) / 32) : 1) : 0;
+    // packed: two mask sets, match bits spread to every other bit (2 K bits per lane and row); quad: per half-warp, K = 32
+    const size_t dyn = !use_mask_ ? 0
+                       : quad ? sizeof(unsigned) * 16 * (size_t)ncodes_ * kWarpsPerBlock * 2 * 2 * 2
+                              : sizeof(unsigned) * 32 * (size_t)ncodes_ * kWarpsPerBlock * (packed ? 2 * ((2 * K + 31) / 32) : 1);
     int nb = 0;
     ANYSEQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, dyn));
     if (nb < 1) { set_last_error("batch kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
-    const long long units = packed ? (npairs + 1) / 2 : npairs;      // work items claimed by the warps
+    const long long units = quad ? (npairs + 3) / 4 : (packed ? (npairs + 1) / 2 : npairs);      // work items claimed by the warps
     const int grid = (int)std::min<long long>((long long)nb * sm_count, (units + kWarpsPerBlock - 1) / kWarpsPerBlock);
     ba.sp = sp;
     ba.gap_init = sc.gap_init;

@@ -51,5 +51,7 @@ __device__ __forceinline__ int batch_code(const uint8_t* __restrict__ base, int 
 using BatchKernelFn = void (*)(const BatchArgs);
 // packed 16-bit kernels (batch_x2.cu): two pairs of equal shape per warp; nullptr if K is not instantiated
 BatchKernelFn pick_batch_x2_kernel(int mode, bool affine, int K);
+// four pairs per warp (16 lanes x 32 columns per pair of pairs): column sequences of at most 512 symbols
+BatchKernelFn pick_batch_x4_kernel(int mode, bool affine);
 
 }  // namespace anyseq

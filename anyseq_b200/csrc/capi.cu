@@ -79,6 +79,7 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
     else if (n == "batch_chunk_pairs" && value >= 1) t.batch_chunk_pairs = value;
     else if (n == "batch_copy_threads" && value >= 1) t.batch_copy_threads = value;
     else if (n == "batch_packed") t.batch_packed = value != 0;
+    else if (n == "batch_quad") t.batch_quad = value != 0;
     else if (n == "align_with_score") t.align_with_score = value != 0;
     else {
         set_last_error("unknown option " + n);

@@ -49,6 +49,7 @@ struct Tuning {
     bool align_with_score = true;
     int batch_chunk_bytes = 64 << 20;    // host batches: packed symbols per pipeline chunk
     int batch_chunk_pairs = 1 << 18;     // host batches: pairs per pipeline chunk
+    bool batch_quad = true;              // packed batches with columns <= 512: four pairs per warp (half-warps)
     bool batch_packed = true;            // batches: two pairs per warp in 16-bit halves when the scores fit
     int batch_copy_threads = 4;          // host batches: threads staging caller memory into pinned slots   // anyseq_align also computes the optimal score (one more m*n pass)
 };

@@ -787,7 +787,11 @@ def test_batch_packed_16bit_kernels(aligner, oracle):
                     A.linear_scoring_scheme(3, -2, -4)):
             for mode in MODES:
                 aligner.set_option("batch_packed", 1)
-                got, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)
+                got, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)        # four pairs per warp where the columns fit
+                aligner.set_option("batch_quad", 0)
+                got2, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)       # two pairs per warp
+                aligner.set_option("batch_quad", 1)
+                assert (got == got2).all(), (lq, ls, mode, sch, np.flatnonzero(got != got2)[:5])
                 aligner.set_option("batch_packed", 0)
                 ref, _ = aligner.score_batch(mode, qd, qo, sd, so, sch)
                 aligner.set_option("batch_packed", 1)
