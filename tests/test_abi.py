@@ -48,7 +48,7 @@ def test_sass_is_sm100a_with_dpx():
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", hot, capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "Function : " + hot in sass, "hot kernel not found in the library (mangled name changed?)"
     n_dpx = sass.count("VIADDMNMX") + sass.count("VIMNMX3")
-    assert n_dpx >= 500 and sass.count("VIMNMX3") >= 100 and sass.count("IMAD") >= 500 and "R2P" in sass, (n_dpx, sass.count("IMAD"))
+    assert n_dpx >= 500 and sass.count("VIMNMX3") >= 50 and sass.count("IMAD") >= 500 and "R2P" in sass, (n_dpx, sass.count("IMAD"))
     # its decoupled sibling (FORM=1: narrow and single-band launches): four VIADDMNMX per cell, no VIMNMX3 in the cells
     dec = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0ELi1EEEvNS_10KernelArgsE",
                           capi.LIB_PATH], capture_output=True, text=True).stdout
