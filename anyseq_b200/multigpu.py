@@ -28,12 +28,13 @@ def _strip_cols(width: int, sm_count: int = 148) -> int:
 
 def column_slices(n: int, world: int, align: int = 1024, rows: int = 0, strip_cols: int = 0, lag_rows: int = 100,
                   sm_count: int = 148):
-    """slices of [0, n), boundaries rounded to `align` columns.  rows == 0: equal slices.  rows > 0 (one long pair as
-    a wavefront over the ranks): rank r can only start when the wavefront has crossed the slices before it, so equal
-    slices leave rank 0 idle at the end and make the last rank the critical path; the slices shrink geometrically
-    instead so that ALL ranks finish together.  With f = (strips of a slice) * lag_rows / rows the fill of a slice
-    relative to its work, a slice is 1 / (1 + f) of its left neighbour; the makespan drops from C + world * fill to
-    about C + (world + 1) / 2 * fill (4.6 Mbp on 8 GPUs: 7 % less)."""
+    """slices of [0, n), boundaries rounded to `align` columns.  rows == 0 (default, what bench.py uses): equal slices.
+    rows > 0: slices that shrink geometrically from rank to rank (a slice is 1 / (1 + f) of its left neighbour, f = strips
+    of a slice * lag_rows / rows), capped at two warps per scheduler.  The idea -- later ranks start later, so give them
+    less -- does NOT pay while every strip of a slice has its own warp: the time of such a slice is rows x (time per
+    row of a strip) whatever its width (measured on 8 B200s, tools/chain_probe.py: 606 208 and 544 768 columns both take
+    831 ms alone), so the makespan is the pace of a strip plus the start delay of the last rank either way (988 ms with
+    equal slices, 1011 ms with shrinking ones).  Kept for launches that run several bands per slice."""
     weights = [1.0] * world
     cap = float(n)
     if rows > 0 and world > 1:

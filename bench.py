@@ -387,7 +387,7 @@ def main():
     al = A.Aligner(local_rank)
     info = al.device_info()
 
-    slices = column_slices(n, world, rows=m)      # shrinking slices: all ranks of the wavefront finish together
+    slices = column_slices(n, world)              # equal slices (see multigpu.column_slices for why not shrinking ones)
     c0, c1 = slices[rank]
     h_q = torch.from_numpy(q).pin_memory()
     h_s = torch.from_numpy(np.ascontiguousarray(s[c0:c1])).pin_memory()
