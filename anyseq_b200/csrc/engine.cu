@@ -178,19 +178,19 @@ static KernelFn pick_kernel(bool local, bool affine, int K, bool mask, bool trac
     return affine ? get_strip_kernel_01(K, mask, form) : get_strip_kernel_00(K, mask, form);
 }
 
-// Cell form of a launch (strip_kernel.cuh: 0 = coupled, 1 = decoupled, 2 = mixed).  Measured on a B200 with the warps of
-// a scheduler on adjacent strips, semiglobal Gotoh, GCUPS, coupled / decoupled / mixed: 4.6 Mbp pair, three warps per
-// scheduler: 3853 / 3885 / 3974 (local: 3315 / 3038 / 3505); 575 k-column slice, two per scheduler: 2846 / 3195 / 3159;
-// lone warps (K = 32 slice): 2214 / 2885 / 2753; 1 Mbp x 1 Mbp: 2500 / 3157 / 2654.  So: the mixed cells where a launch
-// has enough strips for three warps per scheduler over several rounds (ALU-pipe work 253 instead of 285 instructions
-// per 64 cells, and two other warps to hide the coupled rows' chain), the decoupled cells everywhere else.
+// Cell form of a launch (strip_kernel.cuh: 0 = coupled, 1 = decoupled, 2 = mixed).  Measured on B200s with the warps of a
+// scheduler on adjacent strips, semiglobal Gotoh, GCUPS, coupled / decoupled / mixed: 4.6 Mbp pair, three warps per
+// scheduler: 3853 / 3864-3885 on four different boxes / 3974 on one box, 3753-3758 on three others (local Gotoh:
+// 3315 / 3038 / 3302-3505); 575 k-column slice, two per scheduler: 2846 / 3195 / 3159; lone warps (K = 32 slice):
+// 2214 / 2885 / 2753; 1 Mbp x 1 Mbp: 2500 / 3157 / 2654.  So: the decoupled cells everywhere -- they are the fastest or
+// within 2 % of it and the most repeatable -- except for wide LOCAL Gotoh launches, whose decoupled cell needs one more
+// instruction; those run the mixed cells.
 static int pick_form(const Tuning& tune, bool affine, bool mask, int K, long long strips_total, int sm_count, bool local)
 {
-    (void)local;
     const bool has_coupled = affine && mask && K >= 8;
     if (tune.cell_form == 0 || tune.cell_form == 1) return has_coupled ? tune.cell_form : 1;
     if (tune.cell_form == 2) return (has_coupled && K >= 16) ? 2 : 1;
-    return (has_coupled && K >= 16 && strips_total >= 24LL * sm_count) ? 2 : 1;
+    return (has_coupled && K >= 16 && local && strips_total >= 24LL * sm_count) ? 2 : 1;
 }
 
 // rows per lane and step of the kernel variant (strip_kernel.cuh: StripRows)

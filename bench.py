@@ -42,11 +42,11 @@ sys.path.insert(0, ROOT)
 SCORING = dict(same=2, diff=-1, gap_init=-2, gap_extend=-1)
 MODE = "semiglobal"
 OPS_PER_CELL_AFFINE = 7        # algorithmic 32-bit integer ops per Gotoh cell
-# what the strip kernel actually issues per Gotoh cell at full width (mixed cell form -- even rows coupled, odd rows
-# decoupled --, K = 32, two-row tiles; counted in the SASS of the unguarded step loop with tools/sass_stats.py: 446
-# instructions, 253 on the ALU pipe, per 64 cells)
-ISSUED_PER_CELL = 446 / 64.0
-ALU_PER_CELL = 253 / 64.0
+# what the strip kernel actually issues per Gotoh cell at full width (decoupled cell form, K = 32, two-row tiles; counted
+# in the SASS of the unguarded step loop with tools/sass_stats.py: 445 instructions, 285 on the ALU pipe, per 64 cells;
+# ncu on the whole launch: 7.14 warp-instructions per 32 cells, ALU pipe 94 % busy)
+ISSUED_PER_CELL = 445 / 64.0
+ALU_PER_CELL = 285 / 64.0
 METRIC = "GCUPS (score-only ecoli x sboydii affine)"
 
 

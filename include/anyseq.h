@@ -117,12 +117,16 @@ const char* anyseq_last_error(void);
  * in rows, persistent blocks per SM, dependency-wait watchdog in ms. */
 int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int blocks_per_sm, int watchdog_ms);
 
-/* Named options: "cols_per_lane", "band_rows", "blocks_per_sm", "watchdog_ms",
- * "force_generic" (1: byte-register kernels even for small alphabets),
+/* Named options: "cols_per_lane", "band_rows", "blocks_per_sm" (warps per scheduler of the strip kernels, 1-3),
+ * "watchdog_ms" (> 0), "band_slack" (band height = slack * lag * resident warps when a launch has more strips than
+ * warps; default 2), "cell_form" (-1 = per launch, 0 = coupled, 1 = decoupled, 2 = mixed Gotoh cells: identical
+ * results, different instruction mixes -- see DESIGN.md 3.1),
+ * "force_generic" (1: byte-register kernels even for small alphabets), "force_affine" (1: the score path runs the
+ * Gotoh kernels even for gap_init == 0 -- must equal the linear kernels; testing),
  * "align_with_score" (0: anyseq_align skips the extra score pass),
  * "batch_chunk_bytes" / "batch_chunk_pairs" / "batch_copy_threads" (pipeline of
  * anyseq_score_batch with host buffers), "batch_packed" (0: never use the 16-bit two-pairs-per-warp
- * batch kernels),
+ * batch kernels), "batch_quad" (0: never use the four-pairs-per-warp variant of them),
  * "local_end_cell" (1: local scores also fill end_i/end_j with the cell the
  * reference's get_score_pos() reports -- src/scoring.impala:103-110 with the
  * slot order of src/scoring_cpu.impala:48-73; runs the single-row kernels,

@@ -43,13 +43,13 @@ def test_sass_is_sm100a_with_dpx():
     from anyseq_b200 import capi
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    # the headline kernel: strip_kernel<LOCAL=0, AFFINE=1, K=32, MASK=1, TRACK=0, FORM=2> (six template arguments)
-    hot = "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0ELi2EEEvNS_10KernelArgsE"
+    # the mixed-cell kernel (wide local Gotoh launches): strip_kernel<LOCAL=1, AFFINE=1, K=32, MASK=1, TRACK=0, FORM=2>
+    hot = "_ZN6anyseq12strip_kernelILb1ELb1ELi32ELb1ELb0ELi2EEEvNS_10KernelArgsE"
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", hot, capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "Function : " + hot in sass, "hot kernel not found in the library (mangled name changed?)"
     n_dpx = sass.count("VIADDMNMX") + sass.count("VIMNMX3")
     assert n_dpx >= 500 and sass.count("VIMNMX3") >= 50 and sass.count("IMAD") >= 500 and "R2P" in sass, (n_dpx, sass.count("IMAD"))
-    # its decoupled sibling (FORM=1: narrow and single-band launches): four VIADDMNMX per cell, no VIMNMX3 in the cells
+    # the headline kernel (FORM=1, decoupled cells): four VIADDMNMX per cell, no VIMNMX3 in the cells
     dec = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6anyseq12strip_kernelILb0ELb1ELi32ELb1ELb0ELi1EEEvNS_10KernelArgsE",
                           capi.LIB_PATH], capture_output=True, text=True).stdout
     assert dec.count("VIADDMNMX") >= 1000
