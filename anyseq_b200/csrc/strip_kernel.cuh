@@ -942,13 +942,15 @@ strip_kernel(const KernelArgs a)
     // the static assignment): every item only waits on lower-numbered items, which
     // were claimed earlier by warps that are resident, so no wait can be circular.
     int jcur = 0;
-    // First round: static.  CTA b gets items [b F / G, (b + 1) F / G) (F = a.first_items, G = gridDim.x: every SM gets its
+    // First round: static.  CTA b gets items [ceil(b F / G), ceil((b + 1) F / G)) (F = a.first_items, G = gridDim.x: every SM gets its
     // share even when there are fewer items than warps); inside the CTA the items go to the schedulers in runs, so the warps
     // of one scheduler (w, w + 4, w + 8) work on neighbouring strips.  A warp without an item claims one dynamically.
     long long item;
     {
-        const long long lo = (long long)blockIdx.x * a.first_items / gridDim.x;
-        const int cnt = (int)((long long)(blockIdx.x + 1) * a.first_items / gridDim.x - lo);
+        // (rounded up: when the items do not divide evenly, the LAST CTAs get one item less -- the last item of a launch is
+        // its ragged strip, the slowest one, and this way it tends to have a scheduler to itself)
+        const long long lo = ((long long)blockIdx.x * a.first_items + gridDim.x - 1) / gridDim.x;
+        const int cnt = (int)(((long long)(blockIdx.x + 1) * a.first_items + gridDim.x - 1) / gridDim.x - lo);
         const int sch = warp & 3, slot = warp >> 2;
         const int base = cnt >> 2, rem = cnt & 3;
         const int mine = base + (sch < rem ? 1 : 0);           // items of this scheduler
