@@ -81,6 +81,7 @@ int anyseq_ctx_set_option(anyseq_ctx* ctx, const char* name, int value)
     else if (n == "batch_packed") t.batch_packed = value != 0;
     else if (n == "batch_quad") t.batch_quad = value != 0;
     else if (n == "align_with_score") t.align_with_score = value != 0;
+    else if (n == "small_model") t.small_model = value != 0;
     else {
         set_last_error("unknown option " + n);
         return ANYSEQ_ERR_BAD_ARG;

@@ -322,6 +322,7 @@ int Engine::init(int dev)
     if ((env = std::getenv("ANYSEQ_ALIGN_SCORE"))) tune.align_with_score = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_FORCE_GENERIC"))) tune.force_generic = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_CELL_FORM"))) tune.cell_form = std::atoi(env);
+    if ((env = std::getenv("ANYSEQ_SMALL_MODEL"))) tune.small_model = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_BATCH_PACKED"))) tune.batch_packed = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_BATCH_QUAD"))) tune.batch_quad = std::atoi(env) != 0;
     if ((env = std::getenv("ANYSEQ_LOCAL_END_CELL"))) tune.local_end_cell = std::atoi(env) != 0;
@@ -349,6 +350,13 @@ void Engine::destroy()
     copy_stream_ = nullptr;
     h_misc_ = nullptr; ev0_ = ev1_ = nullptr; stream_ = nullptr;
 }
+
+#ifdef ANYSEQ_PROFILE
+// measurement builds only (tools/build_variants.sh): per-strip timeline + the time of the strip kernel alone
+static unsigned long long* g_trace = nullptr;
+static cudaEvent_t g_ev_k0 = nullptr, g_ev_k1 = nullptr;
+static int g_trace_strips = 0;
+#endif
 
 int Engine::resident_warps(int K, bool local, bool affine, long long nstrips)
 {
@@ -422,7 +430,7 @@ int Engine::pick_K_levels(int n_total) const
     return 4;
 }
 
-int Engine::pick_K(int n, bool chained) const
+int Engine::pick_K(int n, bool chained, int m, bool affine) const
 {
     (void)chained;
     if (tune.cols_per_lane == 4 || tune.cols_per_lane == 8 || tune.cols_per_lane == 16 ||
@@ -435,6 +443,29 @@ int Engine::pick_K(int n, bool chained) const
     const long long want = 7LL * sm_count;             // ~1040 strips on a B200
     for (int K = use_mask_ ? 32 : 16; K > 4; K /= 2)   // generic kernels keep subject bytes in registers: K <= 16
         if ((long long)n / (kWarp * K) >= want) return K;
+    // Small problems -- every strip has a scheduler to itself even at K = 4 -- are bound by the critical path of the strip
+    // chain, not by throughput:  time = a_K * rows + lag_K * strips_K  (the last strip's own rows plus the start-up lag of
+    // every strip before it: lane skew + one 32-row border batch + the L2 hand-over).  Measured on the B200 over nine
+    // shapes from 64 x 9011 to 32348 x 9011 (profiles/r02_c1_table_fit.log; the fit reproduces every entry within 5 %
+    // and ranks the three widths correctly for every shape, linear and Gotoh):
+    //                          linear gaps                        Gotoh
+    //      K   rows/step   a_K (ns/row)  lag_K (us/strip)   a_K (ns/row)  lag_K (us/strip)
+    //      4       2           55.5            9.4              67.4            9.2
+    //      8       4           64             15.5              84             16.2
+    //     16       2           96             11.4             131.8           13.6
+    // e.g. 8087 x 9011 linear (the reference CLI's default): 1185 / 1168 / 1056 us; 8087 x 18022: 1815 / 1742 / 1272 us;
+    // 32348 x 9011: 2646 / 2766 / 3389 us; 1024 x 9011 Gotoh: 769 / 750 / 451 us.
+    if (tune.small_model && m > 0 && use_mask_ && !track_ && (n + kWarp * 4 - 1) / (kWarp * 4) <= 4LL * sm_count) {
+        static const struct { int K; double a_ns[2], lag_ns[2]; } kFit[] = {
+            {4, {55.5, 67.4}, {9400.0, 9200.0}}, {8, {64.0, 84.0}, {15500.0, 16200.0}}, {16, {96.0, 131.8}, {11400.0, 13600.0}}};
+        int best = 4;
+        double tbest = 0.0;
+        for (const auto& f : kFit) {
+            const double t = f.a_ns[affine ? 1 : 0] * m + f.lag_ns[affine ? 1 : 0] * ((n + kWarp * f.K - 1) / (kWarp * f.K));
+            if (f.K == 4 || t < tbest) { best = f.K; tbest = t; }
+        }
+        return best;
+    }
     return 4;
 }
 
@@ -513,6 +544,13 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.ptr, 0, sizeof(int) * 4, stream_));
 #ifdef ANYSEQ_PROFILE
     ANYSEQ_CUDA_CHECK(cudaMemsetAsync(misc_.as<int>() + 20, 0, sizeof(int) * 16, stream_));
+    if (!g_trace) {
+        ANYSEQ_CUDA_CHECK(cudaMalloc(&g_trace, sizeof(unsigned long long) * 4 * kTraceStrips));
+        ANYSEQ_CUDA_CHECK(cudaEventCreate(&g_ev_k0));
+        ANYSEQ_CUDA_CHECK(cudaEventCreate(&g_ev_k1));
+    }
+    ANYSEQ_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, sizeof(unsigned long long) * 4 * kTraceStrips, stream_));
+    g_trace_strips = (int)std::min<long long>(strips_total, kTraceStrips);
 #endif
 
     // launch shape: ONE CTA per SM for the ordinary kernels (nb CTAs of 4 warps for the tracking kernels); with few
@@ -555,8 +593,16 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     ka.strip2job = d_strip2job;
     ka.first_items = first_items;
     void* args[] = {&ka};
+#ifdef ANYSEQ_PROFILE
+    ka.trace = g_trace;
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(g_ev_k0, stream_));
+#endif
     ANYSEQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(wpb_used * kWarp), args,
                                                   mask_smem_bytes(use_mask_, track, ncodes_, K, wpb_used), stream_));
+#ifdef ANYSEQ_PROFILE
+    ANYSEQ_CUDA_CHECK(cudaEventRecord(g_ev_k1, stream_));
+    std::fprintf(stderr, "[anyseq profile] launch: grid=%d warps/CTA=%d items=%lld bands=%d form=%d\n", grid, wpb_used, total, nbands, form);
+#endif
     if (launches) *launches += 2;
     return ANYSEQ_OK;
 }
@@ -636,7 +682,9 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
     ANYSEQ_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     rc = analyse_alphabet(d_q, m, d_s_slice, w);
     if (rc) return rc;
-    const int K = want_edges_ ? 4 : pick_K(w, inbox != nullptr || next_inbox != nullptr);     // edge columns are wanted per 128-column block
+    // edge columns are wanted per 128-column block; whole single-GPU problems may use the small-problem fit (pick_K)
+    const bool whole = !inbox && !next_inbox && col_begin == 0 && col_end == n_total;
+    const int K = want_edges_ ? 4 : pick_K(w, !whole, whole ? m : 0, affine);
     const int SW = kWarp * K;
     const int nstrips = (w + SW - 1) / SW;
 
@@ -714,6 +762,26 @@ int Engine::score_strip_device(const anyseq_scoring& sc, const uint8_t* d_q, int
         std::fprintf(stderr, "[anyseq profile] K=%d batches=%llu cycles/batch: wait=%.0f io=%.0f steps=%.0f | items=%llu "
                              "cycles/item: bandwait=%.0f total=%.0f\n", K, pc[3], pc[0] / nb, pc[1] / nb, pc[2] / nb, pc[6],
                      pc[6] ? (double)pc[4] / pc[6] : 0.0, pc[6] ? (double)pc[5] / pc[6] : 0.0);
+        float pre = 0.f, ker = 0.f, post = 0.f;
+        cudaEventElapsedTime(&pre, ev0_, g_ev_k0);
+        cudaEventElapsedTime(&ker, g_ev_k0, g_ev_k1);
+        cudaEventElapsedTime(&post, g_ev_k1, ev1_);
+        std::fprintf(stderr, "[anyseq profile] phases (us): before the strip kernel %.1f, strip kernel %.1f, after %.1f\n",
+                     pre * 1e3, ker * 1e3, post * 1e3);
+        if (const char* tf = std::getenv("ANYSEQ_TRACE_FILE")) {
+            std::vector<unsigned long long> tr((size_t)4 * g_trace_strips);
+            cudaMemcpy(tr.data(), g_trace, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < g_trace_strips; ++i) if (tr[4 * i]) t0 = std::min(t0, tr[4 * i]);
+            if (FILE* f = std::fopen(tf, "a")) {
+                std::fprintf(f, "{\"m\": %d, \"w\": %d, \"K\": %d, \"kernel_us\": %.1f, \"strips\": [", m, w, K, ker * 1e3);
+                for (int i = 0; i < g_trace_strips; ++i)
+                    std::fprintf(f, "%s[%lld, %lld, %lld, %llu]", i ? ", " : "", (long long)(tr[4 * i] - t0), (long long)(tr[4 * i + 1] - t0),
+                                 (long long)(tr[4 * i + 2] - t0), tr[4 * i + 3]);
+                std::fprintf(f, "]}\n");
+                std::fclose(f);
+            }
+        }
     }
 #endif
     if (out) {

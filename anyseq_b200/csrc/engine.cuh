@@ -46,12 +46,13 @@ struct Tuning {
     bool force_generic = false;     // never use the MASK kernels (testing)
     bool force_affine = false;      // score path: run the Gotoh kernels even for gap_init == 0 (testing: must equal the linear kernels)
     bool local_end_cell = false;    // local scores also report the reference's end cell (single-row kernels)
-    bool align_with_score = true;
+    bool align_with_score = true;   // anyseq_align also computes the optimal score (one more m*n pass)
+    bool small_model = true;        // small problems: strip width from the measured critical-path fit (engine.cu: pick_K)
     int batch_chunk_bytes = 64 << 20;    // host batches: packed symbols per pipeline chunk
     int batch_chunk_pairs = 1 << 18;     // host batches: pairs per pipeline chunk
     bool batch_quad = true;              // packed batches with columns <= 512: four pairs per warp (half-warps)
     bool batch_packed = true;            // batches: two pairs per warp in 16-bit halves when the scores fit
-    int batch_copy_threads = 4;          // host batches: threads staging caller memory into pinned slots   // anyseq_align also computes the optimal score (one more m*n pass)
+    int batch_copy_threads = 4;          // host batches: threads staging caller memory into pinned slots
 };
 
 // word layout of the small device "misc" block
@@ -146,7 +147,7 @@ public:
 
 private:
     int run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K, int* launches);
-    int pick_K(int n, bool chained = false) const;
+    int pick_K(int n, bool chained = false, int m = 0, bool affine = false) const;
     int pick_K_levels(int n_total) const;
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* s, long long n);

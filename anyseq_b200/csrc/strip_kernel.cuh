@@ -77,7 +77,13 @@ struct KernelArgs {
     int strips_total;
     const int* strip2job;
     long long first_items;          // items of the static first round (<= gridDim.x * warps per CTA), spread evenly over the CTAs
+#ifdef ANYSEQ_PROFILE
+    unsigned long long* trace;      // measurement builds: [kTraceStrips][4] = item start, first border batch seen, end of the steps (ns), SM
+#endif
 };
+#ifdef ANYSEQ_PROFILE
+constexpr int kTraceStrips = 4096;
+#endif
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
 {
@@ -549,6 +555,14 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
     }
 #ifdef ANYSEQ_PROFILE
     const long long pf_band = clock64() - pf_item0;
+    const long long pf_slot = J.item_begin + strip;
+    const bool pf_trace = a.trace && band == 0 && pf_slot < kTraceStrips && lane == 0;
+    if (pf_trace) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.trace[4 * pf_slot + 0] = global_timer_ns();
+        a.trace[4 * pf_slot + 3] = smid;
+    }
 #endif
 
     int X[K], F[AFFINE ? K : 1], sc[MASK ? 1 : K];
@@ -809,6 +823,9 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
                 }
             }
             PF_END(pf_wait);
+#ifdef ANYSEQ_PROFILE
+            if (pf_trace && tb == 0) a.trace[4 * pf_slot + 1] = global_timer_ns();
+#endif
             PF_BEGIN();
             sm.in[lane] = make_int2(rec.x + go, rec.z);
             sm.q[r & QM] = MASK ? s_lut[qsym] : qsym;
@@ -846,6 +863,7 @@ __device__ __forceinline__ bool process_item(const Job& J, const int band, const
         atomicAdd(pc + 5, (unsigned long long)(clock64() - pf_item0));
         atomicAdd(pc + 6, 1ull);
     }
+    if (pf_trace) a.trace[4 * pf_slot + 2] = global_timer_ns();
 #endif
 
     // drain: remaining edge rows, bottom border, corner, local maximum

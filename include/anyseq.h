@@ -124,6 +124,8 @@ int anyseq_ctx_tune(anyseq_ctx* ctx, int cols_per_lane, int band_rows, int block
  * "force_generic" (1: byte-register kernels even for small alphabets), "force_affine" (1: the score path runs the
  * Gotoh kernels even for gap_init == 0 -- must equal the linear kernels; testing),
  * "align_with_score" (0: anyseq_align skips the extra score pass),
+ * "small_model" (0: small problems keep 128-column strips instead of the width the measured critical-path
+ * fit prefers -- engine.cu: pick_K),
  * "batch_chunk_bytes" / "batch_chunk_pairs" / "batch_copy_threads" (pipeline of
  * anyseq_score_batch with host buffers), "batch_packed" (0: never use the 16-bit two-pairs-per-warp
  * batch kernels), "batch_quad" (0: never use the four-pairs-per-warp variant of them),
