@@ -6,7 +6,7 @@ The package holds only what the path needs: ``csrc/`` (CUDA kernels + C ABI),
 """
 from .api import (  # noqa: F401
     Aligner, AlignmentResult, BatchStream, ScoringScheme, REFERENCE_SCORING,
-    affine_scoring_scheme, linear_scoring_scheme, cigar, default_aligner, pack2,
+    affine_scoring_scheme, linear_scoring_scheme, cigar, default_aligner, pack2, plan_launch,
     global_alignment_score, semiglobal_alignment_score, local_alignment_score,
     construct_global_alignment, construct_semiglobal_alignment, construct_local_alignment,
 )

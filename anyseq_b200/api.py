@@ -224,6 +224,18 @@ class Aligner:
         return ops.value, mhz.value
 
 
+def plan_launch(mode, lenq: int, lens: int, affine: bool = False, sm_count: int = 148, chained: bool = False) -> dict:
+    """The launch the engine makes for one lenq x lens score-only problem (``anyseq_plan_launch``): strip width, tile
+    height, cell form, bands, grid.  Host logic only -- works without a GPU."""
+    L = capi.load_library()
+    plan = capi.LaunchPlan()
+    m = capi.MODES[mode] if isinstance(mode, str) else int(mode)
+    rc = L.anyseq_plan_launch(int(sm_count), m, int(bool(affine)), int(lenq), int(lens), int(bool(chained)), C.byref(plan))
+    if rc != 0:
+        raise AnyseqError(rc, L.anyseq_last_error().decode())
+    return {name: int(getattr(plan, name)) for name, _ in capi.LaunchPlan._fields_}
+
+
 def pack2(seqs: np.ndarray) -> np.ndarray:
     """(npairs, L) uint8 array of A/C/G/T (either case) -> (npairs, ceil(L/4)) packed bytes: four symbols per byte, least
     significant bits first, every row starting on a byte boundary (the layout anyseq_score_batch_packed2 reads with

@@ -333,6 +333,12 @@ int anyseq_measure_int_peak(anyseq_ctx* ctx, int kind, double* ops_per_s, float*
     return ctx->eng.measure_int_peak(kind, ops_per_s, sm_mhz_est);
 }
 
+int anyseq_plan_launch(int sm_count, int mode, int affine, int lenq, int lens, int chained, anyseq_launch_plan* out)
+{
+    anyseq::Engine planner;           // never init()ed: no device, no buffers -- only the planning members are used
+    return planner.plan_launch(sm_count, mode, affine != 0, lenq, lens, chained != 0, out);
+}
+
 int anyseq_device_info(anyseq_ctx* ctx, int* sm_count, int* resident_warps, char* name64)
 {
     if (!ctx) return ANYSEQ_ERR_BAD_ARG;

@@ -246,6 +246,26 @@ static int fit_blocks_per_sm(KernelFn fn, bool track, bool mask, int ncodes, int
     return 0;
 }
 
+// Grid of a strip-kernel launch with `total` items and nb warps per scheduler: ONE CTA per SM for the ordinary kernels
+// (nb CTAs of 4 warps for the tracking kernels); with few items, just enough warps per CTA that every item of the first
+// round has one, spread evenly over all SMs.
+static void launch_shape(bool track, int nb, int sm_count, long long total, int* grid, int* warps_per_cta, long long* first_items)
+{
+    const int wpb = track ? kWarpsPerBlock : kWarpsPerBlock * nb;
+    int wpb_used = wpb;
+    int g;
+    if (track) {
+        g = (int)std::min<long long>((long long)nb * sm_count, std::max<long long>((total + wpb - 1) / wpb, 1));
+    } else {
+        g = (int)std::min<long long>(sm_count, std::max<long long>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 1));
+        const long long per_cta = (total + g - 1) / g;                   // items of the fullest CTA
+        wpb_used = (int)std::min<long long>(wpb, (per_cta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock);
+    }
+    *grid = g;
+    *warps_per_cta = wpb_used;
+    *first_items = std::min<long long>(total, (long long)g * wpb_used);
+}
+
 // ---------------------------------------------------------------------------
 // alphabet analysis for the MASK kernels.  Symbols are compared as raw bytes
 // (src/align.impala:132), so any equality-preserving recoding is legal: bytes
@@ -491,6 +511,41 @@ int Engine::plan_bands(int max_h, long long strips_total, int resident, int K, b
     return (int)std::max<long long>(1, (max_h + target - 1) / target);
 }
 
+// The launch run_jobs() would make for ONE lenq x lens score-only problem (column-mask kernels, default tuning unless
+// this engine's `tune` says otherwise) on a GPU with `sms` SMs -- host logic only, no CUDA call: what the CPU tests and
+// tools/plan.py look at.  The occupancy query of the real path (fit_blocks_per_sm) is taken as granted; the shipped
+// kernels fit 12 warps per SM.
+int Engine::plan_launch(int sms, int mode, bool affine, int m, int n, bool chained, anyseq_launch_plan* out)
+{
+    if (sms < 1 || m < 1 || n < 1 || mode < 0 || mode > 2 || !out) { set_last_error("bad plan request"); return ANYSEQ_ERR_BAD_ARG; }
+    sm_count = sms;
+    use_mask_ = true;
+    track_ = false;
+    const bool local = mode == ANYSEQ_LOCAL;
+    const int K = pick_K(n, chained, chained ? 0 : m, affine);
+    const long long strips = ((long long)n + kWarp * K - 1) / (kWarp * K);
+    const int form = pick_form(tune, affine, true, K, strips, sms, local);
+    int nb = tune.blocks_per_sm > 0 ? tune.blocks_per_sm : default_blocks_per_sm(K, true, false, 3, strips, sms, form);
+    nb = std::max(1, std::min(nb, kMaxStripWarps / kWarpsPerBlock));
+    const int resident = nb * kWarpsPerBlock * sms;
+    const int nbands = plan_bands(m, strips, resident, K, chained);
+    const int bh = (m + nbands - 1) / nbands;
+    int grid, wpb;
+    long long first;
+    launch_shape(false, nb, sms, (long long)nbands * strips, &grid, &wpb, &first);
+    out->cols_per_lane = K;
+    out->rows_per_step = rows_per_step(K, true, false);
+    out->cell_form = form;
+    out->strips = (int)std::min<long long>(strips, 0x7fffffff);
+    out->warps_per_scheduler = nb;
+    out->bands = nbands;
+    out->band_rows = std::max(32, (bh + 31) / 32 * 32);
+    out->grid = grid;
+    out->warps_per_cta = wpb;
+    out->first_items = first;
+    return ANYSEQ_OK;
+}
+
 // Launch init + strip kernels for a job list that is already in host memory.
 int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, bool affine, int K,
                      int* launches)
@@ -513,8 +568,6 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     if (!track) want = std::min(want, kMaxStripWarps / kWarpsPerBlock);
     const int nb = fit_blocks_per_sm(fn, track, use_mask_, ncodes_, K, want);
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
-    const int wpb = track ? kWarpsPerBlock : kWarpsPerBlock * nb;          // warps per CTA
-    const int ctas_per_sm = track ? nb : 1;
     const int resident = nb * kWarpsPerBlock * sm_count;
 
     // bands: the same number for every job of the launch (items are ordered band, job, strip)
@@ -555,16 +608,9 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
 
     // launch shape: ONE CTA per SM for the ordinary kernels (nb CTAs of 4 warps for the tracking kernels); with few
     // items, just enough warps per CTA that every item of the first round has one, spread evenly over all SMs
-    int wpb_used = wpb;
-    int grid;
-    if (track) {
-        grid = (int)std::min<long long>((long long)ctas_per_sm * sm_count, std::max<long long>((total + wpb - 1) / wpb, 1));
-    } else {
-        grid = (int)std::min<long long>(sm_count, std::max<long long>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 1));
-        const long long per_cta = (total + grid - 1) / grid;                   // items of the fullest CTA
-        wpb_used = (int)std::min<long long>(wpb, (per_cta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock);
-    }
-    const long long first_items = std::min<long long>(total, (long long)grid * wpb_used);
+    int wpb_used, grid;
+    long long first_items;
+    launch_shape(track, nb, sm_count, total, &grid, &wpb_used, &first_items);
 
     {
         int maxlen = 1;

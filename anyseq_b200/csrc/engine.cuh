@@ -128,6 +128,8 @@ public:
     int score_batch_packed2_host(const anyseq_scoring& sc, const anyseq_packed_batch& b, int32_t* scores,
                                  anyseq_result* out);
     int measure_int_peak(int kind, double* ops_per_s, float* sm_mhz);
+    // launch planning without a device (engine.cu); usable on an Engine that was never init()ed
+    int plan_launch(int sms, int mode, bool affine, int m, int n, bool chained, anyseq_launch_plan* out);
 
     int inbox_create(int rows, Inbox** out, void* handle64);
     int inbox_open(const void* handle64, int rows, Inbox** out);

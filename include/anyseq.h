@@ -326,6 +326,26 @@ int anyseq_measure_int_peak(anyseq_ctx* ctx, int kind, double* ops_per_s, float*
 /* Device properties the bench reports. */
 int anyseq_device_info(anyseq_ctx* ctx, int* sm_count, int* resident_warps, char* name64);
 
+/* The launch the engine makes for ONE lenq x lens score-only problem on a GPU with sm_count SMs (148 on a B200):
+ * strip width, tile height, cell form, bands and grid.  Pure host logic -- needs no device and no context -- so the
+ * planner can be tested on a CPU-only machine and inspected from tools (tools/plan.py).  It answers for the column-mask
+ * kernels (alphabets of at most 31 shared symbols) with default tuning; chained != 0: the problem is one rank's column
+ * slice of a multi-GPU wavefront.  This replaces what the reference fixes at compile time (BLOCK_WIDTH / BLOCK_HEIGHT,
+ * src/mapping_acc.impala:1-12) and its per-anti-diagonal launch loop (src/iteration_acc.impala:120-172). */
+typedef struct anyseq_launch_plan {
+    int32_t cols_per_lane;        /* K: a strip is 32 * K subject columns wide */
+    int32_t rows_per_step;        /* R: query rows a lane relaxes per anti-diagonal step */
+    int32_t cell_form;            /* 0 coupled, 1 decoupled, 2 mixed */
+    int32_t strips;
+    int32_t warps_per_scheduler;  /* 1..3: resident warps = 4 * this * sm_count */
+    int32_t bands;                /* row bands; 1 when every strip has a warp of its own */
+    int32_t band_rows;
+    int32_t grid;                 /* CTAs (one per SM at most) */
+    int32_t warps_per_cta;
+    int64_t first_items;          /* (band, strip) items assigned statically; the rest is claimed from a counter */
+} anyseq_launch_plan;
+int anyseq_plan_launch(int sm_count, int mode, int affine, int lenq, int lens, int chained, anyseq_launch_plan* out);
+
 #ifdef __cplusplus
 }
 #endif

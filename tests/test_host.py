@@ -287,3 +287,36 @@ def test_sharded_traceback_gather_gloo():
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         assert r.stdout.count("ok") == 2
+
+
+def test_launch_planner_without_a_device():
+    """anyseq_plan_launch: the engine's launch planning (strip width, tile height, bands, grid) is host logic and runs
+    without a GPU.  The expectations are the measured optima recorded in profiles/r02_summary.md."""
+    import anyseq_b200 as A
+    # BASELINE configs[1]: the whole-genome pair -- widest strips, three warps per scheduler, decoupled Gotoh cells
+    p = A.plan_launch("semiglobal", 4641652, 4600000, affine=True)
+    assert (p["cols_per_lane"], p["rows_per_step"], p["cell_form"], p["warps_per_scheduler"]) == (32, 2, 1, 3)
+    assert p["strips"] == (4600000 + 1023) // 1024 and p["grid"] == 148 and p["warps_per_cta"] == 12
+    assert p["bands"] > 1 and p["band_rows"] % 32 == 0 and p["bands"] * p["band_rows"] >= 4641652
+    assert p["first_items"] == 148 * 12
+    # wide LOCAL Gotoh launches take the mixed cells
+    assert A.plan_launch("local", 4641652, 4600000, affine=True)["cell_form"] == 2
+    # one rank's slice of the 8-GPU wavefront: 1124 strips of 512 columns, two warps per scheduler, ONE band
+    p = A.plan_launch("semiglobal", 4641652, 575488, affine=True, chained=True)
+    assert (p["cols_per_lane"], p["strips"], p["warps_per_scheduler"], p["bands"]) == (16, 1124, 2, 1)
+    assert p["first_items"] == 1124 and p["grid"] == 148 and p["warps_per_cta"] == 8
+    # small problems: strip width from the measured critical-path fit (profiles/r02_c1_table_fit.log)
+    expect = {(8087, 9011, False): 16, (8087, 18022, False): 16, (64, 9011, False): 16, (1024, 9011, False): 16,
+              (8087, 128, False): 4, (16174, 9011, False): 4, (32348, 9011, False): 4,
+              (8087, 9011, True): 4, (8087, 18022, True): 16, (1024, 9011, True): 16, (32348, 9011, True): 4, (2048, 2048, True): 4}
+    for (m, n, affine), K in expect.items():
+        p = A.plan_launch("semiglobal" if affine else "global", m, n, affine=affine)
+        assert p["cols_per_lane"] == K, (m, n, affine, p)
+        assert p["bands"] == 1 and p["strips"] == -(-n // (32 * K)) and p["first_items"] == p["strips"]
+        assert p["grid"] == min(148, -(-p["strips"] // 4)) and p["warps_per_cta"] == 4
+    # ... but never for a rank of a multi-GPU wavefront (its rows are shared with the other ranks' slices)
+    assert A.plan_launch("global", 8087, 9011, chained=True)["cols_per_lane"] == 4
+    # a smaller GPU gets a smaller grid and narrower strips for the same problem
+    assert A.plan_launch("semiglobal", 4641652, 4600000, affine=True, sm_count=74)["grid"] == 74
+    with pytest.raises(A.AnyseqError):
+        A.plan_launch("global", 0, 10)
