@@ -511,6 +511,23 @@ int Engine::plan_bands(int max_h, long long strips_total, int resident, int K, b
     return (int)std::max<long long>(1, (max_h + target - 1) / target);
 }
 
+// More strips than warps even with three warps per scheduler: the launch runs in bands, and the warps go through the
+// (band, strip) items in rounds -- the last round may be nearly empty.  1 Mbp x 1 Mbp (1953 strips of 512 columns): three
+// warps per scheduler = 2 bands = 3906 items = 2.2 rounds of 1776 warps, 2585 GCUPS; two per scheduler = 3 bands = 5859
+// items = 4.95 rounds of 1184, 3166 GCUPS (profiles/r02_perf_1m_warps_per_scheduler.log).  So: the fill of the rounds times
+// the full-width rate of the two shapes (3883 vs 3736 GCUPS on the 4.6 Mbp pair, which keeps three: 22.8 rounds).
+int Engine::balance_warps(int nb, int max_h, long long strips_total, int K, bool chained) const
+{
+    if (nb < 3 || tune.blocks_per_sm > 0 || strips_total <= (long long)nb * kWarpsPerBlock * sm_count) return nb;
+    auto rate = [&](int w) {
+        const long long resident = (long long)w * kWarpsPerBlock * sm_count;
+        const long long items = (long long)plan_bands(max_h, strips_total, (int)resident, K, chained) * strips_total;
+        const long long rounds = (items + resident - 1) / resident;
+        return (double)items / (double)(rounds * resident) * (w == 3 ? 1.04 : 1.0);
+    };
+    return rate(2) > rate(3) ? 2 : 3;
+}
+
 // The launch run_jobs() would make for ONE lenq x lens score-only problem (column-mask kernels, default tuning unless
 // this engine's `tune` says otherwise) on a GPU with `sms` SMs -- host logic only, no CUDA call: what the CPU tests and
 // tools/plan.py look at.  The occupancy query of the real path (fit_blocks_per_sm) is taken as granted; the shipped
@@ -527,6 +544,7 @@ int Engine::plan_launch(int sms, int mode, bool affine, int m, int n, bool chain
     const int form = pick_form(tune, affine, true, K, strips, sms, local);
     int nb = tune.blocks_per_sm > 0 ? tune.blocks_per_sm : default_blocks_per_sm(K, true, false, 3, strips, sms, form);
     nb = std::max(1, std::min(nb, kMaxStripWarps / kWarpsPerBlock));
+    nb = balance_warps(nb, m, strips, K, chained);
     const int resident = nb * kWarpsPerBlock * sms;
     const int nbands = plan_bands(m, strips, resident, K, chained);
     const int bh = (m + nbands - 1) / nbands;
@@ -564,15 +582,15 @@ int Engine::run_jobs(std::vector<Job>& jobs, const ScoreParams& sp, bool local, 
     KernelFn fn = pick_kernel(local, affine, K, use_mask_, track_ && local, form);
     if (!fn) { set_last_error("unsupported columns-per-lane"); return ANYSEQ_ERR_BAD_ARG; }
     const bool track = track_ && local;
+    bool chained = false;
+    for (const Job& j : jobs) chained = chained || j.in != nullptr || j.out != nullptr;
     int want = tune.blocks_per_sm > 0 ? tune.blocks_per_sm : default_blocks_per_sm(K, use_mask_, track, track ? 6 : 3, strips_total, sm_count, form);
-    if (!track) want = std::min(want, kMaxStripWarps / kWarpsPerBlock);
+    if (!track) want = balance_warps(std::min(want, kMaxStripWarps / kWarpsPerBlock), max_h, strips_total, K, chained);
     const int nb = fit_blocks_per_sm(fn, track, use_mask_, ncodes_, K, want);
     if (nb < 1) { set_last_error("strip kernel does not fit on an SM"); return ANYSEQ_ERR_UNSUPPORTED; }
     const int resident = nb * kWarpsPerBlock * sm_count;
 
     // bands: the same number for every job of the launch (items are ordered band, job, strip)
-    bool chained = false;
-    for (const Job& j : jobs) chained = chained || j.in != nullptr || j.out != nullptr;
     const int nbands = plan_bands(max_h, strips_total, resident, K, chained);
     for (Job& j : jobs) {
         const int bh = (j.h + nbands - 1) / nbands;

@@ -154,6 +154,7 @@ private:
     int analyse_alphabet(const uint8_t* d_q, long long m, const uint8_t* d_s, long long n);
     int analyse_alphabet_host(const uint8_t* q, long long m, const uint8_t* s, long long n);
     int plan_bands(int max_h, long long strips_total, int resident, int K, bool chained) const;
+    int balance_warps(int nb, int max_h, long long strips_total, int K, bool chained) const;
     int launch_batch(const anyseq_scoring& sc, const ScoreParams& sp, bool affine, BatchArgs& ba, int max_long,
                      int max_short, cudaStream_t st);
 

@@ -316,6 +316,12 @@ def test_launch_planner_without_a_device():
         assert p["grid"] == min(148, -(-p["strips"] // 4)) and p["warps_per_cta"] == 4
     # ... but never for a rank of a multi-GPU wavefront (its rows are shared with the other ranks' slices)
     assert A.plan_launch("global", 8087, 9011, chained=True)["cols_per_lane"] == 4
+    # more strips than warps: two or three warps per scheduler by how full the rounds of items are
+    # (profiles/r02_perf_1m_warps_per_scheduler.log: 1 Mbp x 1 Mbp 3166 GCUPS with two, 2585 with three)
+    p = A.plan_launch("semiglobal", 1000000, 1000000, affine=True)
+    assert (p["cols_per_lane"], p["strips"], p["warps_per_scheduler"], p["bands"], p["warps_per_cta"]) == (16, 1954, 2, 3, 8)
+    # the 2-GPU slice of the whole-genome pair keeps three (as measured in the N = 2 bench line)
+    assert A.plan_launch("semiglobal", 4641652, 2300000, affine=True, chained=True)["warps_per_scheduler"] == 3
     # a smaller GPU gets a smaller grid and narrower strips for the same problem
     assert A.plan_launch("semiglobal", 4641652, 4600000, affine=True, sm_count=74)["grid"] == 74
     with pytest.raises(A.AnyseqError):
